@@ -1,0 +1,151 @@
+/* pea_b200.h -- C ABI of libpea_b200.so (sm_100a only).
+ *
+ * The reference (OPPO-Mente-Lab/PEA-Diffusion) is 100 % Python and defines no FFI of its own:
+ * its hot path is reached through two Python protocols (the adapter nn.Module and diffusers' attention
+ * processor).  This header is therefore the boundary the *rebuild* defines; each entry point cites the reference
+ * statement(s) whose arithmetic it replaces.  All file:line citations are relative to the reference tree.
+ *
+ * Conventions (every function):
+ *   - extern "C", plain C types.  Pointers named d_* / inside descriptors are DEVICE pointers
+ *     (tensor.data_ptr()); descriptor structs themselves live in HOST memory.
+ *   - `stream` is a cudaStream_t / CUstream passed as void* (torch.cuda.current_stream().cuda_stream).
+ *   - Stream-ordered, no host synchronisation, never allocates or frees caller-visible memory: outputs and
+ *     workspaces are allocated by the caller; `*_workspace_bytes` report sizes.
+ *   - Returns 0 on success, a negative PEA_E* code otherwise; pea_last_error() gives a thread-local message.
+ *   - There is no CPU fallback: without an sm_100 device every compute entry point fails with PEA_ENODEV / a
+ *     CUDA launch error.
+ */
+#ifndef PEA_B200_H_
+#define PEA_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PEA_B200_VERSION 100 /* 0.1.0 */
+
+enum { PEA_OK = 0, PEA_EINVAL = -1, PEA_ECUDA = -2, PEA_ENODEV = -3, PEA_EUNSUPPORTED = -4 };
+typedef enum { PEA_F32 = 0, PEA_F16 = 1, PEA_BF16 = 2 } pea_dtype;
+
+int pea_version(void);
+const char* pea_last_error(void);
+/* Number of kernels this library has launched in the calling process (bench.py's `gpu_launches`). */
+long long pea_launch_count(void);
+
+/* ----------------------------------------------------------------------------------------------------------
+ * KD loss: base + output-level + feature-level masked MSE and its gradient, one pass.
+ * Replaces train_sdxl_zh.py:400-405 (L0), :416-421 (L1), :423-441 (L2) and train_sd_zh.py:218-272.
+ *
+ * A tap contributes   term = group_scale * mean_b( mean_chw( (s - t)^2 * w_b ) )   [+ the same with t2, w2]
+ * and, when d_grad != NULL,  d_grad = grad_scale * d(term)/ds  (teacher tensors get no gradient).
+ * `out` (device, 4 + 2*ntaps floats): [0..2] = L0, L1, L2 as the reference logs them (L2 unweighted),
+ * [3] = L0 + L1 + feature_weight * L2, [4+i] = tap i's unweighted term, [4+ntaps+i] = 1.0 if tap i was finite
+ * and counted, 0.0 if it was skipped (train_sd_zh.py:246-268 semantics, only when skip_nonfinite != 0).
+ * -------------------------------------------------------------------------------------------------------- */
+#define PEA_KD_MAX_TAPS 16
+typedef struct {
+  const void* d_student;   /* [B, numel_per_sample], contiguous */
+  const void* d_teacher;   /* same shape */
+  const void* d_teacher2;  /* optional second target for the same student tensor (noise_pred: eps and eps_T) */
+  void* d_grad;            /* optional, same shape/dtype as student */
+  const float* d_weight;   /* [B] per-sample weight for (s - t)^2, e.g. zh_b or 1 - zh_b */
+  const float* d_weight2;  /* [B] per-sample weight for (s - t2)^2 (with d_teacher2) */
+  long long numel_per_sample;
+  int group;               /* 0: L0 (base), 1: L1 (output KD), 2: L2 (feature KD) -- for the (s,t) pair */
+  int group2;              /* group of the (s,t2) pair */
+} pea_kd_tap;
+
+size_t pea_kd_workspace_bytes(const pea_kd_tap* taps, int ntaps, int B);
+int pea_kd_mse_fwd_bwd(const pea_kd_tap* taps, int ntaps, int B, pea_dtype dtype, float feature_weight,
+                       float grad_scale, int skip_nonfinite, void* d_workspace, float* d_out, void* stream);
+/* Backward fix-up: d_grad *= (*d_upstream) * counted_flag; exits immediately on device when the factor is 1.
+ * Needed only when autograd's upstream gradient is not the `grad_scale` assumed by the fused pass. */
+int pea_kd_scale_grads(const pea_kd_tap* taps, int ntaps, int B, pea_dtype dtype, const float* d_upstream,
+                       const float* d_out, void* stream);
+
+/* ----------------------------------------------------------------------------------------------------------
+ * attn2 core: softmax(q k^T * scale) v per head, keys resident in shared memory.
+ * Replaces diffusers AttnProcessor2_0's F.scaled_dot_product_attention call as reached from
+ * train_sdxl_zh.py:397,415 / train_sd_zh.py:215,231 / tests/test_sdxl_zh.py:384-391.
+ *   q, o, dq, do : [B, N, H*d] rows of stride ld_q elements (head h occupies columns [h*d, (h+1)*d))
+ *   k, v         : [B, L, H*d] rows of stride ld_kv elements, batch stride bs_kv elements (K|V may interleave)
+ *   dk, dv       : fp32, same indexing as k, v with ld_dkv / bs_dkv; ACCUMULATED into (caller zero-fills)
+ * L <= 80 (77 for CLIP; 52/64/32 for the other encoders), d in {64} (+{40,80,160}: see DESIGN.md).
+ * -------------------------------------------------------------------------------------------------------- */
+typedef struct {
+  int B, N, L, H, d;
+  float scale;
+  pea_dtype dtype;         /* PEA_BF16 or PEA_F16 */
+  const void* d_q; long long ld_q;
+  const void* d_k; const void* d_v; long long ld_kv, bs_kv;
+  void* d_o; long long ld_o;
+  /* backward only */
+  const void* d_do; long long ld_do;
+  void* d_dq; long long ld_dq;
+  float* d_dk; float* d_dv; long long ld_dkv, bs_dkv;
+} pea_attn2_desc;
+
+int pea_attn2_fwd(const pea_attn2_desc* desc, void* stream);
+int pea_attn2_bwd(const pea_attn2_desc* desc, void* stream);
+
+/* ----------------------------------------------------------------------------------------------------------
+ * Tensor-core GEMM (tcgen05 + TMEM accumulators, TMA-fed), the building block of the adapter
+ * (train_sdxl_zh.py:58-67 forward and its autograd backward) and of the attn2 K/V projections
+ * (AttnProcessor2_0: attn.to_k / attn.to_v) and their context gradient.
+ *
+ *   C[m, n] = sum_k A(m, k) * B(n, k)                      m < M, n < N, k < K
+ *   A stored [M, K] row-major (a_kmajor = 1, lda = row stride) or [K, M] row-major (a_kmajor = 0);
+ *   B stored [N, K] row-major (b_kmajor = 1)               or [K, N] row-major (b_kmajor = 0).
+ * Operands are 16-bit planes; with nsplit = S > 1 the true operand is A[0] + A[1] + ... (bf16 split of an fp32
+ * value) and the kernel accumulates the S(S+1)/2 most significant cross products -- the fp32-accurate mode.
+ * Epilogue:  v = alpha * acc [+ bias[n]] [* gelu'(aux[m, n])] [+ rowadd[(m / rowadd_group), n] * rowadd_scale]
+ *            out0[m, n] (=|+=) v          (raw, any dtype)                        -- optional
+ *            out1 planes   = split_S1( act ? gelu(v) : v )                         -- optional
+ * -------------------------------------------------------------------------------------------------------- */
+typedef struct {
+  int M, N, K;
+  pea_dtype in_dtype;       /* PEA_BF16 or PEA_F16 (nsplit > 1 requires PEA_BF16) */
+  int nsplit;               /* 1..3 */
+  const void* d_A[3]; int a_kmajor; long long lda;
+  const void* d_B[3]; int b_kmajor; long long ldb;
+  float alpha;
+  const float* d_bias;
+  const void* d_aux; pea_dtype aux_dtype; long long ldaux;
+  const float* d_rowadd; int rowadd_group; float rowadd_scale;
+  int act;                  /* 0: identity, 1: exact-erf GELU applied to out1 */
+  void* d_out0; pea_dtype out0_dtype; long long ldo0; int out0_accumulate;
+  void* d_out1[3]; int out1_nsplit; pea_dtype out1_dtype; long long ldo1;
+} pea_gemm_desc;
+
+int pea_gemm(const pea_gemm_desc* desc, void* stream);
+
+/* ----------------------------------------------------------------------------------------------------------
+ * Row-wise helpers of the adapter (LayerNorm of train_sdxl_zh.py:47,60; torch.mean(x, 1) of :66; the
+ * bias gradient; operand splitting) and the CFG-dropout select of train_sdxl_zh.py:392-395.
+ * -------------------------------------------------------------------------------------------------------- */
+int pea_layernorm_fwd(const void* d_x, pea_dtype x_dtype, const float* d_gamma, const float* d_beta, int M, int D,
+                      float eps, void* const d_y_planes[3], int nsplit, pea_dtype plane_dtype, float* d_mean,
+                      float* d_rstd, void* stream);
+/* dgamma/dbeta are ACCUMULATED (+=) so two calls (cond + uncond) can share them; dx optional. */
+int pea_layernorm_bwd(const void* d_x, pea_dtype x_dtype, const float* d_dy, const float* d_gamma,
+                      const float* d_mean, const float* d_rstd, int M, int D, float* d_dgamma, float* d_dbeta,
+                      float* d_dx, void* stream);
+/* planes = split_S(x): x fp32/bf16/fp16 [rows, cols] with row stride ld -> S dense planes of plane_dtype. */
+int pea_split_planes(const void* d_x, pea_dtype x_dtype, long long rows, long long cols, long long ld,
+                     void* const d_planes[3], int nsplit, pea_dtype plane_dtype, void* stream);
+/* out[b, n] = mean_l (x[b*L + l, n] (+ res[b*L + l, n])), fp32 in/out (x1 of train_sdxl_zh.py:64-66). */
+int pea_mean_tokens(const float* d_x, const void* d_res, pea_dtype res_dtype, int B, int L, int D, float* d_out,
+                    void* stream);
+/* out[n] += sum_m x[m, n]  (bias gradient). */
+int pea_colsum_accum(const void* d_x, pea_dtype x_dtype, int M, int N, long long ld, float* d_out, void* stream);
+/* out[b] = mask[b] ? a[b] : c[b] over rows of `row_elems` elements (CFG dropout), and its backward routing. */
+int pea_cfg_select(const unsigned char* d_mask, const void* d_uncond, const void* d_cond, void* d_out, int B,
+                   long long row_elems, pea_dtype dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PEA_B200_H_ */

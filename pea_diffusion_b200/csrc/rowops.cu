@@ -1,0 +1,242 @@
+// rowops.cu -- the adapter's row-wise pieces and the CFG-dropout select.
+//   LayerNorm(in_dim)                      train_sdxl_zh.py:47,60 / train_sd_zh.py:44,54
+//   torch.mean(x, 1)                       train_sdxl_zh.py:66
+//   where(prompt_mask, uncond, cond)       train_sdxl_zh.py:392-395
+// plus operand splitting (fp32 -> bf16 planes) for the fp32-accurate GEMM mode and the bias/affine gradients.
+// All of these touch <= a few MB per step (M = 2*B*77 rows); they are written for clarity and determinism
+// (fixed-order reductions, no float atomics), not tuned.
+#include "common.cuh"
+
+namespace pea {
+namespace {
+
+template <typename T> __device__ __forceinline__ float ld_as_float(const void* p, long long i) { return to_float(static_cast<const T*>(p)[i]); }
+
+__device__ __forceinline__ float load_any(const void* p, pea_dtype dt, long long i) {
+  switch (dt) {
+    case PEA_F32: return static_cast<const float*>(p)[i];
+    case PEA_F16: return __half2float(static_cast<const __half*>(p)[i]);
+    default: return __bfloat162float(static_cast<const __nv_bfloat16*>(p)[i]);
+  }
+}
+__device__ __forceinline__ void store_any(void* p, pea_dtype dt, long long i, float v) {
+  switch (dt) {
+    case PEA_F32: static_cast<float*>(p)[i] = v; break;
+    case PEA_F16: static_cast<__half*>(p)[i] = __float2half_rn(v); break;
+    default: static_cast<__nv_bfloat16*>(p)[i] = __float2bfloat16_rn(v); break;
+  }
+}
+
+struct Planes { void* p[3]; };
+
+// v -> S planes whose sum reproduces v to ~8*S mantissa bits; plane s holds the rounding residual of planes < s.
+__device__ __forceinline__ void store_split(const Planes& pl, int nsplit, pea_dtype dt, long long i, float v) {
+  float r = v;
+#pragma unroll
+  for (int s = 0; s < 3; ++s) {
+    if (s < nsplit) {
+      float q;
+      if (dt == PEA_F16) { __half h = __float2half_rn(r); static_cast<__half*>(pl.p[s])[i] = h; q = __half2float(h); }
+      else { __nv_bfloat16 h = __float2bfloat16_rn(r); static_cast<__nv_bfloat16*>(pl.p[s])[i] = h; q = __bfloat162float(h); }
+      r -= q;
+    }
+  }
+}
+
+// one warp per row
+__global__ void layernorm_fwd_kernel(const void* __restrict__ x, pea_dtype xdt, const float* __restrict__ gamma,
+                                     const float* __restrict__ beta, int M, int D, float eps, Planes y, int nsplit,
+                                     pea_dtype pdt, float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const long long base = (long long)row * D;
+  float s = 0.f;
+  for (int i = lane; i < D; i += 32) s += load_any(x, xdt, base + i);
+  const float mean = warp_sum(s) / (float)D;
+  float v = 0.f;
+  for (int i = lane; i < D; i += 32) { const float d = load_any(x, xdt, base + i) - mean; v = fmaf(d, d, v); }
+  const float rstd = rsqrtf(warp_sum(v) / (float)D + eps);
+  for (int i = lane; i < D; i += 32) {
+    const float xh = (load_any(x, xdt, base + i) - mean) * rstd;
+    store_split(y, nsplit, pdt, base + i, fmaf(xh, gamma[i], beta[i]));
+  }
+  if (lane == 0) { mean_out[row] = mean; rstd_out[row] = rstd; }
+}
+
+// dgamma[d] += sum_m dy*xhat ; dbeta[d] += sum_m dy.  block (32, 8): 32 columns, rows strided over y; fixed order.
+__global__ void layernorm_bwd_affine_kernel(const void* __restrict__ x, pea_dtype xdt, const float* __restrict__ dy,
+                                            const float* __restrict__ mean, const float* __restrict__ rstd, int M, int D,
+                                            float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  __shared__ float sg[8][33], sb[8][33];
+  const int col = blockIdx.x * 32 + threadIdx.x;
+  float ag = 0.f, ab = 0.f;
+  if (col < D) {
+    for (int m = threadIdx.y; m < M; m += 8) {
+      const float g = dy[(long long)m * D + col];
+      const float xh = (load_any(x, xdt, (long long)m * D + col) - mean[m]) * rstd[m];
+      ag = fmaf(g, xh, ag);
+      ab += g;
+    }
+  }
+  sg[threadIdx.y][threadIdx.x] = ag;
+  sb[threadIdx.y][threadIdx.x] = ab;
+  __syncthreads();
+  if (threadIdx.y == 0 && col < D) {
+    float tg = 0.f, tb = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { tg += sg[i][threadIdx.x]; tb += sb[i][threadIdx.x]; }
+    dgamma[col] += tg;
+    dbeta[col] += tb;
+  }
+}
+
+// dx = rstd * (dy*gamma - mean(dy*gamma) - xhat * mean(dy*gamma*xhat)); one warp per row
+__global__ void layernorm_bwd_dx_kernel(const void* __restrict__ x, pea_dtype xdt, const float* __restrict__ dy,
+                                        const float* __restrict__ gamma, const float* __restrict__ mean,
+                                        const float* __restrict__ rstd, int M, int D, float* __restrict__ dx) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const long long base = (long long)row * D;
+  const float mu = mean[row], rs = rstd[row];
+  float c1 = 0.f, c2 = 0.f;
+  for (int i = lane; i < D; i += 32) {
+    const float g = dy[base + i] * gamma[i];
+    const float xh = (load_any(x, xdt, base + i) - mu) * rs;
+    c1 += g;
+    c2 = fmaf(g, xh, c2);
+  }
+  c1 = warp_sum(c1) / (float)D;
+  c2 = warp_sum(c2) / (float)D;
+  for (int i = lane; i < D; i += 32) {
+    const float g = dy[base + i] * gamma[i];
+    const float xh = (load_any(x, xdt, base + i) - mu) * rs;
+    dx[base + i] = rs * (g - c1 - xh * c2);
+  }
+}
+
+__global__ void split_planes_kernel(const void* __restrict__ x, pea_dtype xdt, long long rows, long long cols, long long ld,
+                                    Planes pl, int nsplit, pea_dtype pdt) {
+  const long long n = rows * cols;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols, c = i - r * cols;
+    store_split(pl, nsplit, pdt, i, load_any(x, xdt, r * ld + c));
+  }
+}
+
+__global__ void mean_tokens_kernel(const float* __restrict__ x, const void* __restrict__ res, pea_dtype rdt, int L, int D,
+                                   float* __restrict__ out) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (n >= D) return;
+  float s = 0.f;
+  for (int l = 0; l < L; ++l) {
+    const long long i = ((long long)b * L + l) * D + n;
+    float v = x[i];
+    if (res) v += load_any(res, rdt, i);
+    s += v;
+  }
+  out[(long long)b * D + n] = s / (float)L;
+}
+
+__global__ void colsum_accum_kernel(const void* __restrict__ x, pea_dtype xdt, int M, int N, long long ld, float* __restrict__ out) {
+  __shared__ float sm[8][33];
+  const int col = blockIdx.x * 32 + threadIdx.x;
+  float a = 0.f;
+  if (col < N)
+    for (int m = threadIdx.y; m < M; m += 8) a += load_any(x, xdt, (long long)m * ld + col);
+  sm[threadIdx.y][threadIdx.x] = a;
+  __syncthreads();
+  if (threadIdx.y == 0 && col < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += sm[i][threadIdx.x];
+    out[col] += t;
+  }
+}
+
+template <typename T>
+__global__ void cfg_select_kernel(const unsigned char* __restrict__ mask, const T* __restrict__ u, const T* __restrict__ c,
+                                  T* __restrict__ out, long long row_elems) {
+  const int b = blockIdx.y;
+  const T* src = mask[b] ? u : c;
+  const long long base = (long long)b * row_elems;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < row_elems; i += (long long)gridDim.x * blockDim.x)
+    out[base + i] = src[base + i];
+}
+
+}  // namespace
+}  // namespace pea
+
+using namespace pea;
+
+extern "C" int pea_layernorm_fwd(const void* d_x, pea_dtype x_dtype, const float* d_gamma, const float* d_beta, int M, int D,
+                                 float eps, void* const d_y_planes[3], int nsplit, pea_dtype plane_dtype, float* d_mean,
+                                 float* d_rstd, void* stream) {
+  PEA_CHECK_ARG(d_x && d_gamma && d_beta && d_y_planes && d_mean && d_rstd, "layernorm_fwd: null pointer");
+  PEA_CHECK_ARG(M >= 1 && D >= 1 && nsplit >= 1 && nsplit <= 3, "layernorm_fwd: bad M/D/nsplit");
+  PEA_CHECK_ARG(plane_dtype != PEA_F32, "layernorm_fwd: planes are 16-bit");
+  Planes pl{};
+  for (int s = 0; s < nsplit; ++s) { PEA_CHECK_ARG(d_y_planes[s], "layernorm_fwd: null plane %d", s); pl.p[s] = d_y_planes[s]; }
+  layernorm_fwd_kernel<<<(M + 3) / 4, 128, 0, (cudaStream_t)stream>>>(d_x, x_dtype, d_gamma, d_beta, M, D, eps, pl, nsplit,
+                                                                    plane_dtype, d_mean, d_rstd);
+  PEA_LAUNCH_CHECK();
+  return PEA_OK;
+}
+
+extern "C" int pea_layernorm_bwd(const void* d_x, pea_dtype x_dtype, const float* d_dy, const float* d_gamma, const float* d_mean,
+                                 const float* d_rstd, int M, int D, float* d_dgamma, float* d_dbeta, float* d_dx, void* stream) {
+  PEA_CHECK_ARG(d_x && d_dy && d_gamma && d_mean && d_rstd && d_dgamma && d_dbeta, "layernorm_bwd: null pointer");
+  PEA_CHECK_ARG(M >= 1 && D >= 1, "layernorm_bwd: bad M/D");
+  layernorm_bwd_affine_kernel<<<(D + 31) / 32, dim3(32, 8), 0, (cudaStream_t)stream>>>(d_x, x_dtype, d_dy, d_mean, d_rstd, M, D,
+                                                                                    d_dgamma, d_dbeta);
+  PEA_LAUNCH_CHECK();
+  if (d_dx) {
+    layernorm_bwd_dx_kernel<<<(M + 3) / 4, 128, 0, (cudaStream_t)stream>>>(d_x, x_dtype, d_dy, d_gamma, d_mean, d_rstd, M, D, d_dx);
+    PEA_LAUNCH_CHECK();
+  }
+  return PEA_OK;
+}
+
+extern "C" int pea_split_planes(const void* d_x, pea_dtype x_dtype, long long rows, long long cols, long long ld,
+                                void* const d_planes[3], int nsplit, pea_dtype plane_dtype, void* stream) {
+  PEA_CHECK_ARG(d_x && d_planes && rows >= 1 && cols >= 1 && ld >= cols, "split_planes: bad arguments");
+  PEA_CHECK_ARG(nsplit >= 1 && nsplit <= 3 && plane_dtype != PEA_F32, "split_planes: bad nsplit/plane dtype");
+  Planes pl{};
+  for (int s = 0; s < nsplit; ++s) { PEA_CHECK_ARG(d_planes[s], "split_planes: null plane %d", s); pl.p[s] = d_planes[s]; }
+  const long long n = rows * cols;
+  const int grid = (int)((n + 255) / 256 < (long long)num_sms() * 16 ? (n + 255) / 256 : (long long)num_sms() * 16);
+  split_planes_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_x, x_dtype, rows, cols, ld, pl, nsplit, plane_dtype);
+  PEA_LAUNCH_CHECK();
+  return PEA_OK;
+}
+
+extern "C" int pea_mean_tokens(const float* d_x, const void* d_res, pea_dtype res_dtype, int B, int L, int D, float* d_out,
+                               void* stream) {
+  PEA_CHECK_ARG(d_x && d_out && B >= 1 && L >= 1 && D >= 1, "mean_tokens: bad arguments");
+  mean_tokens_kernel<<<dim3((D + 127) / 128, B), 128, 0, (cudaStream_t)stream>>>(d_x, d_res, res_dtype, L, D, d_out);
+  PEA_LAUNCH_CHECK();
+  return PEA_OK;
+}
+
+extern "C" int pea_colsum_accum(const void* d_x, pea_dtype x_dtype, int M, int N, long long ld, float* d_out, void* stream) {
+  PEA_CHECK_ARG(d_x && d_out && M >= 1 && N >= 1 && ld >= N, "colsum_accum: bad arguments");
+  colsum_accum_kernel<<<(N + 31) / 32, dim3(32, 8), 0, (cudaStream_t)stream>>>(d_x, x_dtype, M, N, ld, d_out);
+  PEA_LAUNCH_CHECK();
+  return PEA_OK;
+}
+
+extern "C" int pea_cfg_select(const unsigned char* d_mask, const void* d_uncond, const void* d_cond, void* d_out, int B,
+                              long long row_elems, pea_dtype dtype, void* stream) {
+  PEA_CHECK_ARG(d_mask && d_uncond && d_cond && d_out && B >= 1 && row_elems >= 1, "cfg_select: bad arguments");
+  const int gx = (int)((row_elems + 255) / 256 < 64 ? (row_elems + 255) / 256 : 64);
+  if (dtype == PEA_F32)
+    cfg_select_kernel<float><<<dim3(gx, B), 256, 0, (cudaStream_t)stream>>>(d_mask, (const float*)d_uncond, (const float*)d_cond,
+                                                                           (float*)d_out, row_elems);
+  else
+    cfg_select_kernel<uint16_t><<<dim3(gx, B), 256, 0, (cudaStream_t)stream>>>(d_mask, (const uint16_t*)d_uncond,
+                                                                              (const uint16_t*)d_cond, (uint16_t*)d_out, row_elems);
+  PEA_LAUNCH_CHECK();
+  return PEA_OK;
+}
