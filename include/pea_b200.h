@@ -99,16 +99,20 @@ int pea_attn2_bwd(const pea_attn2_desc* desc, void* stream);
  *   C[m, n] = sum_k A(m, k) * B(n, k)                      m < M, n < N, k < K
  *   A stored [M, K] row-major (a_kmajor = 1, lda = row stride) or [K, M] row-major (a_kmajor = 0);
  *   B stored [N, K] row-major (b_kmajor = 1)               or [K, N] row-major (b_kmajor = 0).
- * Operands are 16-bit planes; with nsplit = S > 1 the true operand is A[0] + A[1] + ... (bf16 split of an fp32
- * value) and the kernel accumulates the S(S+1)/2 most significant cross products -- the fp32-accurate mode.
+ * Operands are 16-bit planes; with nsplit_a = Sa > 1 the true operand is A[0] + A[1] + ... (a bf16/fp16 split of an
+ * fp32 value, see pea_split_planes) and likewise for B; the kernel accumulates the cross products A[i] * B[j] with
+ * i + j < max(Sa, Sb), i.e. the most significant ones -- the fp32-accurate mode (Sa = Sb = 2: ~2^-16 relative).
  * Epilogue:  v = alpha * acc [+ bias[n]] [* gelu'(aux[m, n])] [+ rowadd[(m / rowadd_group), n] * rowadd_scale]
  *            out0[m, n] (=|+=) v          (raw, any dtype)                        -- optional
  *            out1 planes   = split_S1( act ? gelu(v) : v )                         -- optional
+ * split_k > 1 partitions the K loop over that many CTAs per tile which add their partial sums atomically; it needs
+ * out0 fp32 with out0_accumulate = 1 (the caller zero-fills or really accumulates) and no out1 / bias / aux.
+ * Leading dimensions are in elements and must be multiples of 8; base pointers 16-byte aligned.
  * -------------------------------------------------------------------------------------------------------- */
 typedef struct {
   int M, N, K;
-  pea_dtype in_dtype;       /* PEA_BF16 or PEA_F16 (nsplit > 1 requires PEA_BF16) */
-  int nsplit;               /* 1..3 */
+  pea_dtype in_dtype;       /* PEA_BF16 or PEA_F16 */
+  int nsplit_a, nsplit_b;   /* 1..3 planes per operand */
   const void* d_A[3]; int a_kmajor; long long lda;
   const void* d_B[3]; int b_kmajor; long long ldb;
   float alpha;
@@ -118,6 +122,7 @@ typedef struct {
   int act;                  /* 0: identity, 1: exact-erf GELU applied to out1 */
   void* d_out0; pea_dtype out0_dtype; long long ldo0; int out0_accumulate;
   void* d_out1[3]; int out1_nsplit; pea_dtype out1_dtype; long long ldo1;
+  int split_k;              /* 0 or 1: none */
 } pea_gemm_desc;
 
 int pea_gemm(const pea_gemm_desc* desc, void* stream);

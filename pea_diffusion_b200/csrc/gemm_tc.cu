@@ -1,0 +1,410 @@
+// gemm_tc.cu -- tcgen05 / TMEM / TMA GEMM with fused epilogues (SURVEY.md kernels K1, K2 and the dContext GEMM).
+//
+//   C[m, n] = sum_k A(m, k) * B(n, k)
+//
+// Used for  * the PEA adapter's Linear chain forward and backward (train_sdxl_zh.py:58-67 and its autograd graph):
+//             bias, exact-erf GELU, GELU', the mean-pool gradient broadcast and the bf16 operand split of the
+//             fp32-accurate mode all live in the epilogue;
+//           * attn2's to_k / to_v projections of the context (diffusers AttnProcessor2_0) and dContext = dK Wk + dV Wv.
+//
+// Structure (one 128 x 128 output tile per CTA, 192 threads):
+//   warp 0      TMA producer: 128B-swizzled [128 x 64] operand tiles, `stages`-deep mbarrier ring
+//   warp 1      TMEM allocator + MMA issuer: one thread issues tcgen05.mma (M128 N128 K16, kind::f16, fp32 accumulate
+//               in TMEM); tcgen05.commit releases smem stages and finally signals the epilogue
+//   warps 2..5  epilogue: tcgen05.ld (each warp its 32-lane TMEM quadrant, thread = output row), fused math, stores
+// Operand majors: K-major tiles come from one {64, 128} TMA box; MN-major tiles (A^T / B^T stored row-major) from two
+// {64, 64} boxes, consumed through MN-major UMMA descriptors -- so dX = dY W and dW = dY^T X need no transposes.
+// fp32-accurate mode: operands are sums of up to 3 bf16 planes; per K step the kernel issues the cross products
+// A[i] B[j], i + j < S.  All planes of a stage share one mbarrier transaction.
+#include "tc05.cuh"
+
+namespace pea {
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 64;
+constexpr int kTileBytes = BM * BK * 2;  // 16 KiB per operand plane per stage
+constexpr int kMaxStages = 6;
+constexpr int kThreads = 192;
+constexpr uint32_t kTmemCols = 128;
+constexpr size_t kSmemBudget = 200 * 1024;
+
+struct GemmParams {
+  CUtensorMap tmA[3];
+  CUtensorMap tmB[3];
+  int M, N, K;
+  int sa, sb;
+  int a_mn, b_mn;
+  int kb_total, kb_per_split;
+  int stages;
+  uint32_t idesc;
+  float alpha;
+  const float* bias;
+  const void* aux; int aux_dtype; long long ldaux;
+  const float* rowadd; int rowadd_group; float rowadd_scale;
+  int act;
+  void* out0; int out0_dtype; long long ldo0; int out0_mode;  // 0 store, 1 +=, 2 atomic add
+  void* out1[3]; int out1_nsplit; int out1_dtype; long long ldo1;
+};
+
+// ---- epilogue helpers: 8 consecutive columns of one row -----------------------------------------------------------
+__device__ __forceinline__ void load8(const void* base, int dtype, long long off, bool vec, int valid, float* f) {
+  if (dtype == PEA_F32) {
+    const float* p = static_cast<const float*>(base) + off;
+    if (vec) {
+      const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+      f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = j < valid ? p[j] : 0.f;
+    }
+  } else if (dtype == PEA_F16) {
+    const __half* p = static_cast<const __half*>(base) + off;
+    if (vec) {
+      const uint4 u = *reinterpret_cast<const uint4*>(p);
+      float2 a = unpack2<__half>(u.x), b = unpack2<__half>(u.y), c = unpack2<__half>(u.z), d = unpack2<__half>(u.w);
+      f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = j < valid ? __half2float(p[j]) : 0.f;
+    }
+  } else {
+    const __nv_bfloat16* p = static_cast<const __nv_bfloat16*>(base) + off;
+    if (vec) {
+      const uint4 u = *reinterpret_cast<const uint4*>(p);
+      float2 a = unpack2<__nv_bfloat16>(u.x), b = unpack2<__nv_bfloat16>(u.y), c = unpack2<__nv_bfloat16>(u.z), d = unpack2<__nv_bfloat16>(u.w);
+      f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = j < valid ? __bfloat162float(p[j]) : 0.f;
+    }
+  }
+}
+
+__device__ __forceinline__ void store8(void* base, int dtype, long long off, bool vec, int valid, const float* f, int mode) {
+  if (dtype == PEA_F32) {
+    float* p = static_cast<float*>(base) + off;
+    if (mode == 2) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (j < valid) atomicAdd(p + j, f[j]);
+    } else if (vec) {
+      float4 a = make_float4(f[0], f[1], f[2], f[3]), b = make_float4(f[4], f[5], f[6], f[7]);
+      if (mode == 1) {
+        const float4 oa = *reinterpret_cast<const float4*>(p), ob = *reinterpret_cast<const float4*>(p + 4);
+        a.x += oa.x; a.y += oa.y; a.z += oa.z; a.w += oa.w; b.x += ob.x; b.y += ob.y; b.z += ob.z; b.w += ob.w;
+      }
+      *reinterpret_cast<float4*>(p) = a;
+      *reinterpret_cast<float4*>(p + 4) = b;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (j < valid) p[j] = (mode == 1 ? p[j] : 0.f) + f[j];
+    }
+  } else if (dtype == PEA_F16) {
+    __half* p = static_cast<__half*>(base) + off;
+    float g[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] = f[j];
+    if (mode == 1) {
+      float o[8];
+      load8(base, dtype, off, vec, valid, o);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] += o[j];
+    }
+    if (vec) {
+      *reinterpret_cast<uint4*>(p) = make_uint4(pack2<__half>(g[0], g[1]), pack2<__half>(g[2], g[3]), pack2<__half>(g[4], g[5]), pack2<__half>(g[6], g[7]));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (j < valid) p[j] = __float2half_rn(g[j]);
+    }
+  } else {
+    __nv_bfloat16* p = static_cast<__nv_bfloat16*>(base) + off;
+    float g[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] = f[j];
+    if (mode == 1) {
+      float o[8];
+      load8(base, dtype, off, vec, valid, o);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] += o[j];
+    }
+    if (vec) {
+      *reinterpret_cast<uint4*>(p) = make_uint4(pack2<__nv_bfloat16>(g[0], g[1]), pack2<__nv_bfloat16>(g[2], g[3]),
+                                                pack2<__nv_bfloat16>(g[4], g[5]), pack2<__nv_bfloat16>(g[6], g[7]));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (j < valid) p[j] = __float2bfloat16_rn(g[j]);
+    }
+  }
+}
+
+__device__ __forceinline__ float round16(float v, int dtype) {
+  return dtype == PEA_F16 ? __half2float(__float2half_rn(v)) : __bfloat162float(__float2bfloat16_rn(v));
+}
+
+__global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t acc_bar;
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int kb_begin = blockIdx.z * p.kb_per_split;
+  const int kb_end = min(p.kb_total, kb_begin + p.kb_per_split);
+  const int nkb = kb_end - kb_begin;  // >= 1 by construction
+  const uint32_t tiles = (smem_u32(smem_raw) + 1023u) & ~1023u;  // 128B swizzle atoms need 1024-byte alignment
+  const uint32_t stage_bytes = (uint32_t)(p.sa + p.sb) * kTileBytes;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < p.sa; ++i) tc::prefetch_tmap(&p.tmA[i]);
+    for (int i = 0; i < p.sb; ++i) tc::prefetch_tmap(&p.tmB[i]);
+    for (int s = 0; s < p.stages; ++s) {
+      tc::mbar_init(smem_u32(&full_bar[s]), 1);
+      tc::mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    tc::mbar_init(smem_u32(&acc_bar), 1);
+    tc::fence_mbar_init();
+  }
+  if (warp == 1) tc::tmem_alloc(smem_u32(&tmem_base_slot), kTmemCols);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      for (int it = 0; it < nkb; ++it) {
+        const int s = it % p.stages;
+        const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+        tc::mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
+        const uint32_t fb = smem_u32(&full_bar[s]);
+        tc::mbar_expect_tx(fb, stage_bytes);
+        const int k0 = (kb_begin + it) * BK;
+        uint32_t dst = tiles + (uint32_t)s * stage_bytes;
+        for (int i = 0; i < p.sa; ++i, dst += kTileBytes) {
+          if (!p.a_mn) tc::tma_load_2d(dst, &p.tmA[i], fb, k0, m0);
+          else { tc::tma_load_2d(dst, &p.tmA[i], fb, m0, k0); tc::tma_load_2d(dst + kTileBytes / 2, &p.tmA[i], fb, m0 + 64, k0); }
+        }
+        for (int j = 0; j < p.sb; ++j, dst += kTileBytes) {
+          if (!p.b_mn) tc::tma_load_2d(dst, &p.tmB[j], fb, k0, n0);
+          else { tc::tma_load_2d(dst, &p.tmB[j], fb, n0, k0); tc::tma_load_2d(dst + kTileBytes / 2, &p.tmB[j], fb, n0 + 64, k0); }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const int S = max(p.sa, p.sb);
+      // per K=16 step: K-major advances 32 B inside the swizzle atom; MN-major advances 16 k-rows = 2048 B
+      const uint32_t a_kstep = p.a_mn ? 2048u : 32u, b_kstep = p.b_mn ? 2048u : 32u;
+      const uint32_t a_lbo = p.a_mn ? (uint32_t)BK * 128u : 16u, b_lbo = p.b_mn ? (uint32_t)BK * 128u : 16u;
+      uint32_t accumulate = 0;
+      for (int it = 0; it < nkb; ++it) {
+        const int s = it % p.stages;
+        const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+        tc::mbar_wait(smem_u32(&full_bar[s]), ph);
+        tc::fence_after_sync();
+        const uint32_t a_base = tiles + (uint32_t)s * stage_bytes;
+        const uint32_t b_base = a_base + (uint32_t)p.sa * kTileBytes;
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          for (int i = 0; i < p.sa; ++i) {
+            const uint64_t da = tc::make_sdesc(a_base + (uint32_t)i * kTileBytes + (uint32_t)k * a_kstep, a_lbo, 1024u);
+            for (int j = 0; j < p.sb && i + j < S; ++j) {
+              const uint64_t db = tc::make_sdesc(b_base + (uint32_t)j * kTileBytes + (uint32_t)k * b_kstep, b_lbo, 1024u);
+              tc::mma_f16_ss(tmem_base, da, db, p.idesc, accumulate);
+              accumulate = 1;
+            }
+          }
+        }
+        tc::mma_commit(smem_u32(&empty_bar[s]));  // stage reusable once these MMAs have read it
+      }
+      tc::mma_commit(smem_u32(&acc_bar));  // accumulator complete
+    }
+  } else {
+    // ===== epilogue: warp w owns TMEM lanes [32*(w%4), +32) = output rows m0 + 32*(w%4) + lane =====
+    const int q = warp & 3;
+    const int row = m0 + q * 32 + lane;
+    const bool row_ok = row < p.M;
+    tc::mbar_wait(smem_u32(&acc_bar), 0);
+    tc::fence_after_sync();
+    const bool al0 = p.out0 && (p.ldo0 % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.out0) & (p.out0_dtype == PEA_F32 ? 31 : 15)) == 0);
+    const bool al1 = p.out1_nsplit > 0 && (p.ldo1 % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.out1[0]) & 15) == 0) &&
+                     (p.out1_nsplit < 2 || (reinterpret_cast<uintptr_t>(p.out1[1]) & 15) == 0) &&
+                     (p.out1_nsplit < 3 || (reinterpret_cast<uintptr_t>(p.out1[2]) & 15) == 0);
+    const bool alx = p.aux && (p.ldaux % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.aux) & (p.aux_dtype == PEA_F32 ? 31 : 15)) == 0);
+    const float* radd = (p.rowadd && row_ok) ? p.rowadd + (long long)(row / p.rowadd_group) * p.N : nullptr;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t v[32];
+      tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+      tc::tmem_ld_wait();
+      if (!row_ok) continue;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int n = n0 + c * 32 + g * 8;
+        if (n >= p.N) break;
+        const int valid = min(8, p.N - n);
+        const bool full = valid == 8;
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = p.alpha * __uint_as_float(v[g * 8 + j]);
+        if (p.bias) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (j < valid) f[j] += p.bias[n + j];
+        }
+        if (p.aux) {
+          float a[8];
+          load8(p.aux, p.aux_dtype, (long long)row * p.ldaux + n, full && alx, valid, a);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] *= gelu_exact_grad(a[j]);
+        }
+        if (radd) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (j < valid) f[j] = fmaf(radd[n + j], p.rowadd_scale, f[j]);
+        }
+        if (p.out0) store8(p.out0, p.out0_dtype, (long long)row * p.ldo0 + n, full && al0, valid, f, p.out0_mode);
+        if (p.out1_nsplit > 0) {
+          if (p.act) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = gelu_exact(f[j]);
+          }
+          for (int s = 0; s < p.out1_nsplit; ++s) {
+            float r[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { r[j] = round16(f[j], p.out1_dtype); f[j] -= r[j]; }
+            store8(p.out1[s], p.out1_dtype, (long long)row * p.ldo1 + n, full && al1, valid, r, 0);
+          }
+        }
+      }
+    }
+  }
+
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc::fence_after_sync();
+    tc::tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+}  // namespace
+
+// ---- host: tensor-map encoding ------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int encode_tmap_16bit(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                      const uint32_t* box, bool fp16) {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    PEA_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres));
+    if (!sym || qres != cudaDriverEntryPointSuccess) {
+      set_error("cuTensorMapEncodeTiled is not available from this driver");
+      return PEA_ENODEV;
+    }
+    fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[5];
+  cuuint32_t bdim[5], estr[5];
+  for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bdim[i] = box[i]; estr[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
+  const CUresult rc = fn(out, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank,
+                         const_cast<void*>(base), gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d, dims %llu x %llu, stride %llu, box %u x %u)", (int)rc, rank,
+              (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 1),
+              (unsigned long long)(rank > 1 ? strides_bytes[0] : 0), box[0], rank > 1 ? box[1] : 1);
+    return PEA_ECUDA;
+  }
+  return PEA_OK;
+}
+
+}  // namespace pea
+
+using namespace pea;
+
+extern "C" int pea_gemm(const pea_gemm_desc* g, void* stream) {
+  PEA_CHECK_ARG(g, "gemm: null descriptor");
+  PEA_CHECK_ARG(g->M >= 1 && g->N >= 1 && g->K >= 1, "gemm: M, N, K must be >= 1 (got %d, %d, %d)", g->M, g->N, g->K);
+  PEA_CHECK_ARG(g->in_dtype == PEA_BF16 || g->in_dtype == PEA_F16, "gemm: operands must be bf16 or fp16 planes");
+  PEA_CHECK_ARG(g->nsplit_a >= 1 && g->nsplit_a <= 3 && g->nsplit_b >= 1 && g->nsplit_b <= 3, "gemm: nsplit_a/b must be 1..3");
+  PEA_CHECK_ARG(g->lda % 8 == 0 && g->ldb % 8 == 0, "gemm: lda/ldb must be multiples of 8 elements (TMA 16-byte strides)");
+  PEA_CHECK_ARG(g->lda >= (g->a_kmajor ? g->K : g->M) && g->ldb >= (g->b_kmajor ? g->K : g->N), "gemm: lda/ldb smaller than the row length");
+  PEA_CHECK_ARG(g->d_out0 || g->out1_nsplit > 0, "gemm: no output requested");
+  PEA_CHECK_ARG(g->out1_nsplit >= 0 && g->out1_nsplit <= 3, "gemm: out1_nsplit must be 0..3");
+  PEA_CHECK_ARG(g->out1_nsplit == 0 || g->out1_dtype != PEA_F32, "gemm: out1 planes are 16-bit");
+  PEA_CHECK_ARG(!g->d_rowadd || g->rowadd_group >= 1, "gemm: rowadd_group must be >= 1");
+
+  GemmParams p{};
+  p.M = g->M; p.N = g->N; p.K = g->K;
+  p.sa = g->nsplit_a; p.sb = g->nsplit_b;
+  p.a_mn = g->a_kmajor ? 0 : 1; p.b_mn = g->b_kmajor ? 0 : 1;
+  const bool fp16 = g->in_dtype == PEA_F16;
+  for (int i = 0; i < p.sa; ++i) {
+    PEA_CHECK_ARG(g->d_A[i] && (reinterpret_cast<uintptr_t>(g->d_A[i]) & 15) == 0, "gemm: A plane %d null or not 16-byte aligned", i);
+    const uint64_t dims[2] = {(uint64_t)(p.a_mn ? g->M : g->K), (uint64_t)(p.a_mn ? g->K : g->M)};
+    const uint64_t str[1] = {(uint64_t)g->lda * 2};
+    const uint32_t box[2] = {64u, p.a_mn ? 64u : 128u};
+    int rc = encode_tmap_16bit(&p.tmA[i], g->d_A[i], 2, dims, str, box, fp16);
+    if (rc != PEA_OK) return rc;
+  }
+  for (int j = 0; j < p.sb; ++j) {
+    PEA_CHECK_ARG(g->d_B[j] && (reinterpret_cast<uintptr_t>(g->d_B[j]) & 15) == 0, "gemm: B plane %d null or not 16-byte aligned", j);
+    const uint64_t dims[2] = {(uint64_t)(p.b_mn ? g->N : g->K), (uint64_t)(p.b_mn ? g->K : g->N)};
+    const uint64_t str[1] = {(uint64_t)g->ldb * 2};
+    const uint32_t box[2] = {64u, p.b_mn ? 64u : 128u};
+    int rc = encode_tmap_16bit(&p.tmB[j], g->d_B[j], 2, dims, str, box, fp16);
+    if (rc != PEA_OK) return rc;
+  }
+  p.kb_total = (g->K + BK - 1) / BK;
+  int splits = g->split_k > 1 ? g->split_k : 1;
+  if (splits > 1) {
+    PEA_CHECK_ARG(g->d_out0 && g->out0_dtype == PEA_F32 && g->out0_accumulate && g->out1_nsplit == 0 && !g->d_bias && !g->d_aux && !g->d_rowadd,
+                  "gemm: split_k needs an accumulating fp32 out0 and no bias/aux/rowadd/out1");
+    if (splits > p.kb_total) splits = p.kb_total;
+  }
+  p.kb_per_split = (p.kb_total + splits - 1) / splits;
+  splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;  // no empty split
+  const size_t stage_bytes = (size_t)(p.sa + p.sb) * kTileBytes;
+  int stages = (int)(kSmemBudget / stage_bytes);
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages > p.kb_per_split) stages = p.kb_per_split < 1 ? 1 : p.kb_per_split;
+  p.stages = stages;
+  p.idesc = tc::make_idesc(fp16 ? 0 : 1, BM, BN, p.a_mn, p.b_mn);
+  p.alpha = g->alpha;
+  p.bias = g->d_bias;
+  p.aux = g->d_aux; p.aux_dtype = g->aux_dtype; p.ldaux = g->ldaux;
+  p.rowadd = g->d_rowadd; p.rowadd_group = g->rowadd_group; p.rowadd_scale = g->rowadd_scale;
+  p.act = g->act;
+  p.out0 = g->d_out0; p.out0_dtype = g->out0_dtype; p.ldo0 = g->ldo0;
+  p.out0_mode = splits > 1 ? 2 : (g->out0_accumulate ? 1 : 0);
+  for (int s = 0; s < g->out1_nsplit; ++s) {
+    PEA_CHECK_ARG(g->d_out1[s], "gemm: out1 plane %d is null", s);
+    p.out1[s] = g->d_out1[s];
+  }
+  p.out1_nsplit = g->out1_nsplit; p.out1_dtype = g->out1_dtype; p.ldo1 = g->ldo1;
+
+  const size_t smem = (size_t)stages * stage_bytes + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    PEA_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemBudget + 1024)));
+    attr_set = true;
+  }
+  dim3 grid((g->N + BN - 1) / BN, (g->M + BM - 1) / BM, splits);
+  gemm_tc_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(p);
+  PEA_LAUNCH_CHECK();
+  return PEA_OK;
+}

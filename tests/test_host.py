@@ -1,0 +1,133 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every symbol the header declares, the product
+refuses host tensors (no CPU fallback), checkpoint-key compatibility, and the data-parallel gradient exchange on a
+world_size-2 gloo group."""
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    src = open(os.path.join(ROOT, "include", "pea_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(pea_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    import ctypes
+    from pea_diffusion_b200 import _lib
+    names = _header_symbols()
+    assert len(names) >= 15
+    dll = ctypes.CDLL(_lib.LIB_PATH)
+    for n in names:
+        assert hasattr(dll, n), f"{n} declared in include/pea_b200.h but not exported"
+    assert sorted(_lib.SYMBOLS) == names, "ctypes binding table and header disagree"
+    assert _lib.lib.pea_version() == 100
+    nm = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "pea_gemm" in nm
+
+
+def test_argument_errors_come_back_as_text_without_a_gpu():
+    import ctypes as C
+    from pea_diffusion_b200 import _lib
+    d = _lib.GemmDesc()
+    assert _lib.lib.pea_gemm(C.byref(d), None) == -1
+    assert b"M, N, K" in _lib.lib.pea_last_error()
+    a = _lib.Attn2Desc()
+    a.B = a.N = a.H = 1
+    a.L = 100
+    assert _lib.lib.pea_attn2_fwd(C.byref(a), None) == -1 and b"L=100" in _lib.lib.pea_last_error()
+
+
+def test_product_refuses_host_tensors():
+    from pea_diffusion_b200 import MLP, PEAAttn2Processor, kd_loss
+    from pea_diffusion_b200._lib import PeaError
+    from pea_diffusion_b200.shell.unet import Attention
+    with pytest.raises(PeaError, match="no CPU fallback"):
+        MLP(64, 80, 96, 128, False)(torch.randn(2, 7, 64))
+    attn = Attention(64, 128, 1, 64).half()
+    with pytest.raises(PeaError, match="no CPU fallback"):
+        PEAAttn2Processor()(attn, torch.randn(1, 16, 64).half(), encoder_hidden_states=torch.randn(1, 77, 128).half())
+    p = torch.randn(2, 4, 8, 8)
+    with pytest.raises(Exception):
+        kd_loss(p, p, p, [], [], torch.tensor([0, 1]))
+
+
+def test_state_dict_keys_match_reference_goldens():
+    from pea_diffusion_b200 import MLP, MLP_Legacy, MLP_SD
+    from tests.util import load_golden, state_dict_of
+    for name, mod in (("adapter_sdxl_small", MLP(64, 80, 96, 128, False)), ("adapter_sd_small", MLP_SD(64, 48, 96)),
+                      ("adapter_sd5_small", MLP_SD(64, 48, 96, num_linear=5)), ("adapter_legacy_small", MLP_Legacy(64, 80, 96, 128, False))):
+        sd = state_dict_of(load_golden(name))
+        assert list(mod.state_dict().keys()) == list(sd.keys()), name
+        mod.load_state_dict(sd, strict=True)
+    full = MLP(1024, 1280, 1024, 2048, False)
+    assert sum(p.numel() for p in full.parameters()) == 6033408  # README.md:11 "only 6M parameters"
+    with pytest.raises(AssertionError):
+        MLP(64, 80, 96, 128, True)  # use_residual needs in_dim == out_dim (train_sdxl_zh.py:45-46)
+
+
+def test_processor_falls_back_outside_contract():
+    """Self-attention / masks / fp32 activations are routed to the stock processor."""
+    from pea_diffusion_b200 import PEAAttn2Processor
+    from pea_diffusion_b200.shell.unet import Attention, StockAttnProcessor
+    torch.manual_seed(0)
+    attn = Attention(64, None, 2, 32)
+    x = torch.randn(1, 16, 64)
+    want = StockAttnProcessor()(attn, x)
+    got = PEAAttn2Processor(fallback=StockAttnProcessor())(attn, x)
+    assert torch.equal(want, got)
+
+
+_DP_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from pea_diffusion_b200.train import GradAllReducer
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+torch.manual_seed(0)
+m = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.GELU(), torch.nn.Linear(16, 4))
+red = GradAllReducer(m.parameters())
+opt = torch.optim.AdamW(m.parameters(), lr=1e-2, weight_decay=0.0)
+g = torch.Generator().manual_seed(100 + rank)
+full = [torch.randn(6, 8, generator=torch.Generator().manual_seed(100 + r)) for r in range(world)]
+for step in range(3):
+    opt.zero_grad(set_to_none=True)
+    m(full[rank]).pow(2).mean().backward()
+    red.finish()
+    opt.step()
+# single-process replay on the concatenated batch must give the same parameters
+torch.manual_seed(0)
+ref = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.GELU(), torch.nn.Linear(16, 4))
+ropt = torch.optim.AdamW(ref.parameters(), lr=1e-2, weight_decay=0.0)
+for step in range(3):
+    ropt.zero_grad(set_to_none=True)
+    ref(torch.cat(full)).pow(2).mean().backward()
+    ropt.step()
+for p, q in zip(m.parameters(), ref.parameters()):
+    assert torch.allclose(p, q, atol=1e-6), (p - q).abs().max()
+flat = torch.cat([p.detach().flatten() for p in m.parameters()])
+gathered = [torch.empty_like(flat) for _ in range(world)]
+dist.all_gather(gathered, flat)
+assert all(torch.equal(gathered[0], t) for t in gathered), "ranks diverged"
+assert red.bytes_per_step == sum(p.numel() * 4 for p in m.parameters())
+dist.destroy_process_group()
+print("ok", rank)
+'''
+
+
+def test_grad_allreduce_world2_gloo(tmp_path):
+    script = tmp_path / "dp_worker.py"
+    script.write_text(_DP_WORKER)
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT="29541", OMP_NUM_THREADS="1")
+        procs.append(subprocess.Popen([sys.executable, str(script), ROOT], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
