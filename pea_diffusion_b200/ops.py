@@ -17,6 +17,51 @@ Tensor = torch.Tensor
 Planes = List[Tensor]
 
 
+class KernelTimer:
+    """Optional per-launch CUDA-event timing of the library's kernels on the launching stream (used by bench.py for the
+    roofline figures).  Disabled by default: zero overhead on the product path."""
+
+    def __init__(self):
+        self.enabled = False
+        self.records = []  # (name, algorithmic_bytes, flops, start_event, end_event)
+
+    def reset(self, enabled: bool) -> None:
+        self.enabled = enabled
+        self.records = []
+
+    def summary(self):
+        """-> {name: {"launches", "ms", "bytes", "flops"}}; call after a device synchronize."""
+        out = {}
+        for name, nbytes, flops, e0, e1 in self.records:
+            r = out.setdefault(name, {"launches": 0, "ms": 0.0, "bytes": 0, "flops": 0})
+            r["launches"] += 1
+            r["ms"] += e0.elapsed_time(e1)
+            r["bytes"] += nbytes
+            r["flops"] += flops
+        return out
+
+
+TIMER = KernelTimer()
+
+
+class _timed:
+    def __init__(self, name: str, nbytes: int, flops: int = 0):
+        self.args = (name, nbytes, flops)
+
+    def __enter__(self):
+        if TIMER.enabled:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if TIMER.enabled:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            TIMER.records.append((*self.args, self.e0, e1))
+        return False
+
+
 def _row_major_2d(t: Tensor) -> None:
     if t.dim() != 2 or t.stride(1) != 1:
         raise ValueError(f"expected a 2-D tensor with unit column stride, got shape {tuple(t.shape)} strides {t.stride()}")
@@ -69,7 +114,11 @@ def gemm(A: Sequence[Tensor], B: Sequence[Tensor], M: int, N: int, K: int, *, a_
         d.d_out1 = planes3(out1)
         d.out1_nsplit, d.out1_dtype, d.ldo1 = len(out1), dtype_code(out1[0].dtype), out1[0].stride(0)
     d.split_k = split_k
-    check(lib.pea_gemm(C.byref(d), stream_ptr(A[0].device)), "pea_gemm")
+    nprod = sum(1 for i in range(len(A)) for j in range(len(B)) if i + j < max(len(A), len(B)))
+    io = 2 * (len(A) * M * K + len(B) * N * K) + (out0.element_size() * M * N if out0 is not None else 0) + \
+        (sum(t.element_size() for t in out1) * M * N if out1 else 0) + (aux.element_size() * M * N if aux is not None else 0)
+    with _timed("gemm", io, 2 * M * N * K * nprod):
+        check(lib.pea_gemm(C.byref(d), stream_ptr(A[0].device)), "pea_gemm")
 
 
 def split_planes(x: Tensor, nsplit: int, plane_dtype: torch.dtype) -> Planes:
@@ -149,7 +198,9 @@ def attn2_fwd(q: Tensor, kv: Tensor, heads: int, scale: float) -> Tensor:
     o = torch.empty(B, N, Cq, device=q.device, dtype=q.dtype)
     d = _attn_desc(q, kv, heads, scale)
     d.d_o, d.ld_o = o.data_ptr(), Cq
-    check(lib.pea_attn2_fwd(C.byref(d), stream_ptr(q.device)), "pea_attn2_fwd")
+    es = q.element_size()
+    with _timed("attn2_fwd", 2 * B * N * Cq * es + 2 * B * L * Cq * es, 4 * B * N * L * Cq):
+        check(lib.pea_attn2_fwd(C.byref(d), stream_ptr(q.device)), "pea_attn2_fwd")
     return o
 
 
@@ -167,7 +218,10 @@ def attn2_bwd(q: Tensor, kv: Tensor, do: Tensor, heads: int, scale: float):
     d.d_dq, d.ld_dq = dq.data_ptr(), Cq
     d.d_dk, d.d_dv = dkv.data_ptr(), dkv.data_ptr() + 4 * Cq
     d.ld_dkv, d.bs_dkv = 2 * Cq, L * 2 * Cq
-    check(lib.pea_attn2_bwd(C.byref(d), stream_ptr(q.device)), "pea_attn2_bwd")
+    es = q.element_size()
+    # read Q, dO, write dQ; read K, V; accumulate dK, dV (fp32 here: 2 * 4 bytes)
+    with _timed("attn2_bwd", 3 * B * N * Cq * es + 2 * B * L * Cq * es + 2 * B * L * Cq * 4, 10 * B * N * L * Cq):
+        check(lib.pea_attn2_bwd(C.byref(d), stream_ptr(q.device)), "pea_attn2_bwd")
     return dq, dkv
 
 
@@ -214,8 +268,14 @@ def kd_mse_fwd_bwd(taps: KdTaps, B: int, dtype: torch.dtype, feature_weight: flo
     ws_bytes = lib.pea_kd_workspace_bytes(taps.arr, taps.n, B)
     ws = torch.empty(max(ws_bytes // 4, 1), device=device, dtype=torch.float32)
     out = torch.empty(4 + 2 * taps.n, device=device, dtype=torch.float32)
-    check(lib.pea_kd_mse_fwd_bwd(taps.arr, taps.n, B, dtype_code(dtype), feature_weight, grad_scale, int(skip_nonfinite),
-                                 ws.data_ptr(), out.data_ptr(), stream_ptr(device)), "pea_kd_mse_fwd_bwd")
+    es = 4 if dtype == torch.float32 else 2
+    nbytes = 0
+    for i in range(taps.n):
+        t = taps.arr[i]
+        nbytes += t.numel_per_sample * B * es * (2 + (1 if t.d_teacher2 else 0) + (1 if t.d_grad else 0))
+    with _timed("kd_mse", nbytes):
+        check(lib.pea_kd_mse_fwd_bwd(taps.arr, taps.n, B, dtype_code(dtype), feature_weight, grad_scale, int(skip_nonfinite),
+                                     ws.data_ptr(), out.data_ptr(), stream_ptr(device)), "pea_kd_mse_fwd_bwd")
     return out
 
 
