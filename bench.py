@@ -252,7 +252,9 @@ def main():
     clocks = ClockSampler(local) if rank == 0 else None
     n0 = _lib.launch_count()
     ops.TIMER.reset(True)
+    torch.cuda.nvtx.range_push("pea_timed")
     ms_step = timed(lambda: trainer.step(dbatch), args.steps)
+    torch.cuda.nvtx.range_pop()
     ops.TIMER.enabled = False
     launches = _lib.launch_count() - n0
     ksum = ops.TIMER.summary()

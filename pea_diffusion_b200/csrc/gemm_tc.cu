@@ -16,6 +16,8 @@
 // {64, 64} boxes, consumed through MN-major UMMA descriptors -- so dX = dY W and dW = dY^T X need no transposes.
 // fp32-accurate mode: operands are sums of up to 3 bf16 planes; per K step the kernel issues the cross products
 // A[i] B[j], i + j < S.  All planes of a stage share one mbarrier transaction.
+#include <stdlib.h>
+
 #include "tc05.cuh"
 
 namespace pea {
@@ -144,6 +146,12 @@ __device__ __forceinline__ float round16(float v, int dtype) {
   return dtype == PEA_F16 ? __half2float(__float2half_rn(v)) : __bfloat162float(__float2bfloat16_rn(v));
 }
 
+// SA / SB: operand plane counts; A_MN / B_MN: operand majors.  Everything the issue loops touch is a compile-time
+// constant or a warp-uniform value: the whole producer / MMA warp runs the loop (uniform control flow keeps address
+// and descriptor arithmetic on the uniform datapath) and only the asynchronous instruction itself is issued by one
+// elected lane.  A single-lane loop with runtime plane / major branches measured ~430 cycles between MMAs (the
+// 128x128x16 MMA itself takes 64): r1 ncu capture profiles/gemm_r1_before.txt.
+template <int SA, int SB, int A_MN, int B_MN>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
@@ -151,18 +159,22 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   __shared__ __align__(8) uint64_t acc_bar;
   __shared__ uint32_t tmem_base_slot;
 
+  constexpr int S = SA > SB ? SA : SB;
+  constexpr uint32_t kStageBytes = (uint32_t)(SA + SB) * kTileBytes;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   const int kb_begin = blockIdx.z * p.kb_per_split;
   const int kb_end = min(p.kb_total, kb_begin + p.kb_per_split);
   const int nkb = kb_end - kb_begin;  // >= 1 by construction
   const uint32_t tiles = (smem_u32(smem_raw) + 1023u) & ~1023u;  // 128B swizzle atoms need 1024-byte alignment
-  const uint32_t stage_bytes = (uint32_t)(p.sa + p.sb) * kTileBytes;
+  const int stages = p.stages;
 
   if (warp == 0 && lane == 0) {
-    for (int i = 0; i < p.sa; ++i) tc::prefetch_tmap(&p.tmA[i]);
-    for (int i = 0; i < p.sb; ++i) tc::prefetch_tmap(&p.tmB[i]);
-    for (int s = 0; s < p.stages; ++s) {
+#pragma unroll
+    for (int i = 0; i < SA; ++i) tc::prefetch_tmap(&p.tmA[i]);
+#pragma unroll
+    for (int i = 0; i < SB; ++i) tc::prefetch_tmap(&p.tmB[i]);
+    for (int s = 0; s < stages; ++s) {
       tc::mbar_init(smem_u32(&full_bar[s]), 1);
       tc::mbar_init(smem_u32(&empty_bar[s]), 1);
     }
@@ -176,55 +188,68 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   const uint32_t tmem_base = tmem_base_slot;
 
   if (warp == 0) {
-    // ===== TMA producer =====
-    if (lane == 0) {
-      for (int it = 0; it < nkb; ++it) {
-        const int s = it % p.stages;
-        const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-        tc::mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
+    // ===== TMA producer (whole warp loops; one elected lane issues) =====
+    int s = 0;
+    uint32_t ph = 0;
+    for (int it = 0; it < nkb; ++it) {
+      tc::mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
+      if (tc::elect_one()) {
         const uint32_t fb = smem_u32(&full_bar[s]);
-        tc::mbar_expect_tx(fb, stage_bytes);
+        tc::mbar_expect_tx(fb, kStageBytes);
         const int k0 = (kb_begin + it) * BK;
-        uint32_t dst = tiles + (uint32_t)s * stage_bytes;
-        for (int i = 0; i < p.sa; ++i, dst += kTileBytes) {
-          if (!p.a_mn) tc::tma_load_2d(dst, &p.tmA[i], fb, k0, m0);
-          else { tc::tma_load_2d(dst, &p.tmA[i], fb, m0, k0); tc::tma_load_2d(dst + kTileBytes / 2, &p.tmA[i], fb, m0 + 64, k0); }
+        const uint32_t dst = tiles + (uint32_t)s * kStageBytes;
+#pragma unroll
+        for (int i = 0; i < SA; ++i) {
+          const uint32_t d = dst + (uint32_t)i * kTileBytes;
+          if (!A_MN) tc::tma_load_2d(d, &p.tmA[i], fb, k0, m0);
+          else { tc::tma_load_2d(d, &p.tmA[i], fb, m0, k0); tc::tma_load_2d(d + kTileBytes / 2, &p.tmA[i], fb, m0 + 64, k0); }
         }
-        for (int j = 0; j < p.sb; ++j, dst += kTileBytes) {
-          if (!p.b_mn) tc::tma_load_2d(dst, &p.tmB[j], fb, k0, n0);
-          else { tc::tma_load_2d(dst, &p.tmB[j], fb, n0, k0); tc::tma_load_2d(dst + kTileBytes / 2, &p.tmB[j], fb, n0 + 64, k0); }
+#pragma unroll
+        for (int j = 0; j < SB; ++j) {
+          const uint32_t d = dst + (uint32_t)(SA + j) * kTileBytes;
+          if (!B_MN) tc::tma_load_2d(d, &p.tmB[j], fb, k0, n0);
+          else { tc::tma_load_2d(d, &p.tmB[j], fb, n0, k0); tc::tma_load_2d(d + kTileBytes / 2, &p.tmB[j], fb, n0 + 64, k0); }
         }
       }
+      __syncwarp();
+      if (++s == stages) { s = 0; ph ^= 1u; }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
-      const int S = max(p.sa, p.sb);
-      // per K=16 step: K-major advances 32 B inside the swizzle atom; MN-major advances 16 k-rows = 2048 B
-      const uint32_t a_kstep = p.a_mn ? 2048u : 32u, b_kstep = p.b_mn ? 2048u : 32u;
-      const uint32_t a_lbo = p.a_mn ? (uint32_t)BK * 128u : 16u, b_lbo = p.b_mn ? (uint32_t)BK * 128u : 16u;
-      uint32_t accumulate = 0;
-      for (int it = 0; it < nkb; ++it) {
-        const int s = it % p.stages;
-        const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-        tc::mbar_wait(smem_u32(&full_bar[s]), ph);
-        tc::fence_after_sync();
-        const uint32_t a_base = tiles + (uint32_t)s * stage_bytes;
-        const uint32_t b_base = a_base + (uint32_t)p.sa * kTileBytes;
+    // ===== MMA issuer (whole warp loops; one elected lane issues tcgen05.mma / tcgen05.commit) =====
+    // per K=16 step: K-major advances 32 B inside the swizzle atom; MN-major advances 16 k-rows = 2048 B
+    constexpr uint32_t kAStep = A_MN ? 2048u : 32u, kBStep = B_MN ? 2048u : 32u;
+    constexpr uint32_t kALbo = A_MN ? (uint32_t)BK * 128u : 16u, kBLbo = B_MN ? (uint32_t)BK * 128u : 16u;
+    // descriptor = constant high word | (lbo field) | 14-bit (address >> 4); only the address part changes
+    constexpr uint64_t kADescHi = ((uint64_t)(kALbo >> 4) << 16) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
+    constexpr uint64_t kBDescHi = ((uint64_t)(kBLbo >> 4) << 16) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
+    const uint32_t idesc = p.idesc;
+    int s = 0;
+    uint32_t ph = 0;
+    for (int it = 0; it < nkb; ++it) {
+      tc::mbar_wait(smem_u32(&full_bar[s]), ph);
+      tc::fence_after_sync();
+      if (tc::elect_one()) {
+        const uint32_t a_base = (tiles + (uint32_t)s * kStageBytes) >> 4;  // smem < 256 KiB: fits the 14-bit field
+        const uint32_t b_base = a_base + (uint32_t)SA * (kTileBytes >> 4);
 #pragma unroll
         for (int k = 0; k < BK / 16; ++k) {
-          for (int i = 0; i < p.sa; ++i) {
-            const uint64_t da = tc::make_sdesc(a_base + (uint32_t)i * kTileBytes + (uint32_t)k * a_kstep, a_lbo, 1024u);
-            for (int j = 0; j < p.sb && i + j < S; ++j) {
-              const uint64_t db = tc::make_sdesc(b_base + (uint32_t)j * kTileBytes + (uint32_t)k * b_kstep, b_lbo, 1024u);
-              tc::mma_f16_ss(tmem_base, da, db, p.idesc, accumulate);
-              accumulate = 1;
+#pragma unroll
+          for (int i = 0; i < SA; ++i) {
+#pragma unroll
+            for (int j = 0; j < SB; ++j) {
+              if (i + j < S) {
+                const uint64_t da = kADescHi | (uint64_t)(a_base + (uint32_t)((i * kTileBytes + k * kAStep) >> 4));
+                const uint64_t db = kBDescHi | (uint64_t)(b_base + (uint32_t)((j * kTileBytes + k * kBStep) >> 4));
+                tc::mma_f16_ss(tmem_base, da, db, idesc, (k == 0 && i == 0 && j == 0) ? (uint32_t)(it > 0) : 1u);
+              }
             }
           }
         }
-        tc::mma_commit(smem_u32(&empty_bar[s]));  // stage reusable once these MMAs have read it
+        tc::mma_commit(smem_u32(&empty_bar[s]));                      // stage reusable once these MMAs have read it
+        if (it == nkb - 1) tc::mma_commit(smem_u32(&acc_bar));        // accumulator complete
       }
-      tc::mma_commit(smem_u32(&acc_bar));  // accumulator complete
+      __syncwarp();
+      if (++s == stages) { s = 0; ph ^= 1u; }
     }
   } else {
     // ===== epilogue: warp w owns TMEM lanes [32*(w%4), +32) = output rows m0 + 32*(w%4) + lane =====
@@ -293,6 +318,40 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     tc::fence_after_sync();
     tc::tmem_dealloc(tmem_base, kTmemCols);
   }
+}
+
+template <int SA, int SB, int A_MN, int B_MN>
+int launch(const GemmParams& p, dim3 grid, size_t smem, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    PEA_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<SA, SB, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemBudget + 1024)));
+    attr_set = true;
+  }
+  gemm_tc_kernel<SA, SB, A_MN, B_MN><<<grid, kThreads, smem, st>>>(p);
+  PEA_LAUNCH_CHECK();
+  return PEA_OK;
+}
+
+template <int SA, int SB>
+int dispatch_major(const GemmParams& p, dim3 grid, size_t smem, cudaStream_t st) {
+  switch (p.a_mn * 2 + p.b_mn) {
+    case 0: return launch<SA, SB, 0, 0>(p, grid, smem, st);
+    case 1: return launch<SA, SB, 0, 1>(p, grid, smem, st);
+    case 2: return launch<SA, SB, 1, 0>(p, grid, smem, st);
+    default: return launch<SA, SB, 1, 1>(p, grid, smem, st);
+  }
+}
+
+int dispatch(const GemmParams& p, dim3 grid, size_t smem, cudaStream_t st) {
+  switch (p.sa * 4 + p.sb) {
+    case 1 * 4 + 1: return dispatch_major<1, 1>(p, grid, smem, st);
+    case 2 * 4 + 1: return dispatch_major<2, 1>(p, grid, smem, st);
+    case 1 * 4 + 2: return dispatch_major<1, 2>(p, grid, smem, st);
+    case 2 * 4 + 2: return dispatch_major<2, 2>(p, grid, smem, st);
+    case 3 * 4 + 3: return dispatch_major<3, 3>(p, grid, smem, st);
+  }
+  set_error("gemm: plane combination (%d, %d) is not instantiated (supported: 1x1, 2x1, 1x2, 2x2, 3x3)", p.sa, p.sb);
+  return PEA_EUNSUPPORTED;
 }
 
 }  // namespace
@@ -398,13 +457,6 @@ extern "C" int pea_gemm(const pea_gemm_desc* g, void* stream) {
   p.out1_nsplit = g->out1_nsplit; p.out1_dtype = g->out1_dtype; p.ldo1 = g->ldo1;
 
   const size_t smem = (size_t)stages * stage_bytes + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
-    PEA_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemBudget + 1024)));
-    attr_set = true;
-  }
   dim3 grid((g->N + BN - 1) / BN, (g->M + BM - 1) / BM, splits);
-  gemm_tc_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(p);
-  PEA_LAUNCH_CHECK();
-  return PEA_OK;
+  return dispatch(p, grid, smem, static_cast<cudaStream_t>(stream));
 }

@@ -21,13 +21,17 @@ DEV = "cuda:0"
 PEAK = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))
 
 
-def timeit(fn, iters, warm=10):
+WARM = 10
+
+
+def timeit(fn, iters, warm=None):
     scratch = torch.empty(256 << 20, device=DEV, dtype=torch.uint8)
-    for _ in range(warm):
+    for _ in range(WARM if warm is None else warm):
         fn()
     ts = []
     for _ in range(iters):
         scratch.fill_(1)  # L2 flush
+        torch.cuda._sleep(600000)  # ~0.3 ms of GPU spin so the host is ahead of the GPU when the timed launch is enqueued
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); fn(); e1.record()
         e1.synchronize()
@@ -41,7 +45,11 @@ def main():
     ap.add_argument("--iters", type=int, default=50)
     ap.add_argument("--out", default="gpurun_out/microbench.jsonl")
     ap.add_argument("--only", default="")
+    ap.add_argument("--warm", type=int, default=10)
+    ap.add_argument("--filter", default="", help="comma list: gemm shape names / attn 'N:C' pairs to keep")
     args = ap.parse_args()
+    global WARM
+    WARM = args.warm
     os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
     out = open(args.out, "w")
 
@@ -49,11 +57,14 @@ def main():
         print(json.dumps(kw)); out.write(json.dumps(kw) + "\n"); out.flush()
 
     dt = torch.bfloat16
+    keep = [x for x in args.filter.split(",") if x]
     if not args.only or "attn" in args.only:
         B = 8
         for (C, H) in ((640, 10), (1280, 20)):
             for N in (1024, 4096, 16384):
-                for L in ((77, 64, 52) if (N == 4096 and C == 640) else (77,)):
+                if keep and f"{N}:{C}" not in keep:
+                    continue
+                for L in ((77, 64, 52) if (N == 4096 and C == 640 and not keep) else (77,)):
                     q = torch.randn(B, N, C, device=DEV, dtype=dt)
                     kv = torch.randn(B, L, 2 * C, device=DEV, dtype=dt)
                     do = torch.randn(B, N, C, device=DEV, dtype=dt)
@@ -83,6 +94,8 @@ def main():
                   ("adapter_fwd_1024", 1232, 1024, 1024, 1, 1, True), ("adapter_fwd_fc", 1232, 2048, 1280, 1, 1, True),
                   ("adapter_fwd_1024_fp32x2", 1232, 1024, 1024, 2, 2, True), ("big_4096", 4096, 4096, 4096, 1, 1, True)]
         for name, M, N, K, sa, sb, bk in shapes:
+            if keep and name not in keep:
+                continue
             A = [torch.randn(M, K, device=DEV, dtype=dt) for _ in range(sa)]
             Bm = [torch.randn(N, K, device=DEV, dtype=dt) if bk else torch.randn(K, N, device=DEV, dtype=dt) for _ in range(sb)]
             o = torch.empty(M, N, device=DEV, dtype=dt)
