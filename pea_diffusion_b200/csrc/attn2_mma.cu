@@ -13,6 +13,8 @@
 // kernel (HBM-bound, 80-wide key tile) is the first implementation and where the tcgen05 variant stands.
 //
 // Algorithmic bytes (e = 2): fwd 2*B*N*C*e + 2*B*L*C*e ; bwd 3*B*N*C*e + 2*B*L*C*e + 2*B*L*C*4.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace pea {
@@ -405,7 +407,22 @@ int validate(const pea_attn2_desc* a, bool bwd, AttnParams& p) {
 }  // namespace
 }  // namespace pea
 
+namespace pea {
+int attn2_fwd_tc(const pea_attn2_desc* a, cudaStream_t st);   // attn2_tc.cu
+bool attn2_fwd_tc_eligible(const pea_attn2_desc* a);
+}  // namespace pea
+
 using namespace pea;
+
+// PEA_ATTN2_IMPL=mma forces the warp-MMA kernels (A/B measurements); default: tcgen05 forward when head_dim == 64.
+static bool use_tc_path() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PEA_ATTN2_IMPL");
+    v = (e && e[0] == 'm') ? 0 : 1;
+  }
+  return v == 1;
+}
 
 #define PEA_DISPATCH_ATTN(LAUNCH)                                                                           \
   do {                                                                                                       \
@@ -434,6 +451,7 @@ extern "C" int pea_attn2_fwd(const pea_attn2_desc* desc, void* stream) {
   int rc = validate(desc, false, p);
   if (rc != PEA_OK) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (use_tc_path() && attn2_fwd_tc_eligible(desc)) return attn2_fwd_tc(desc, st);
   PEA_DISPATCH_ATTN(launch_fwd);
 }
 

@@ -1,0 +1,329 @@
+// attn2_tc.cu -- tcgen05 / TMEM / TMA forward of the fused cross-attention core for head_dim 64 (every SDXL attn2).
+//
+// Replaces F.scaled_dot_product_attention inside diffusers' AttnProcessor2_0 (reached from train_sdxl_zh.py:397,415 and
+// tests/test_sdxl_zh.py:384-391) for the <= 80-key regime.  HBM-bound: Q streams in once, O streams out once; the
+// projected context K|V of one (batch, head) -- 2 x 80 x 64 x 2 B = 20 KiB -- is TMA'd into shared memory once per CTA.
+//
+// Persistent-style grid: <= 3 CTAs per SM, each CTA walks a CONTIGUOUS range of (batch, head, 128-row query tile) work
+// items (query tile fastest), so Q prefetch never drains and K|V is reloaded only when (batch, head) changes.
+// 192 threads per CTA:
+//   warp 0      TMA producer: K, V tiles (rows >= L zero-filled by TMA) on a (batch, head) change, Q tiles into a
+//               2-deep ring
+//   warp 1      TMEM allocator + MMA issuer:  S = Q K^T   (tcgen05.mma SS, M128 N80 K64  -> TMEM cols [0,80))
+//                                             O = P V     (tcgen05.mma TS, M128 N64 K80  -> TMEM cols [64,128))
+//   warps 2..5  softmax + epilogue, thread = query row (TMEM lane): tcgen05.ld S, single-pass softmax (all keys are in
+//               the tile: no online rescaling, no cross-thread reduction at all), unnormalised P -> bf16 -> tcgen05.st
+//               over S's own columns [0,40), later tcgen05.ld O, scale by 1/rowsum, 128B-swizzled staging tile,
+//               TMA store (clips the N tail).
+// TMEM: 128 columns per CTA (S [0,80) aliased by P [0,40); O [64,128) is only written after S is dead).
+// Algorithmic bytes per CTA tile: 128 x 64 x 2 B in + the same out; FLOPs 4 x 128 x 80 x 64.
+#include "tc05.cuh"
+
+namespace pea {
+namespace {
+
+constexpr int kQT = 128;                 // query rows per tile
+constexpr int kD = 64;                   // head dim
+constexpr int kLP = 80;                  // padded key count
+constexpr int kThreads = 192;
+constexpr uint32_t kTmemCols = 128;
+constexpr uint32_t kQBytes = kQT * kD * 2;      // 16 KiB
+constexpr uint32_t kKVBytes = kLP * kD * 2;     // 10 KiB each
+constexpr uint32_t kOffK = 0, kOffV = 10240, kOffQ0 = 20480, kOffQ1 = kOffQ0 + kQBytes, kOffO = kOffQ1 + kQBytes;
+constexpr uint32_t kSmemBytes = kOffO + kQBytes + 1024;  // + alignment slack
+
+struct FwdParams {
+  CUtensorMap tmQ, tmKV, tmO;
+  int B, N, L, H, C;
+  int tiles_per_bh, total_tiles, tiles_per_cta;
+  float scale_log2;
+  uint32_t idesc_s, idesc_o;
+};
+
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]),
+               "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads, 3) attn2_fwd_tc_kernel(const __grid_constant__ FwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_kv, kv_empty, q_full[2], q_empty[2], s_full, p_ready, o_full, tmem_free;
+  __shared__ uint32_t tmem_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
+
+  // ---- this CTA's contiguous range of work items; item = bh * tiles_per_bh + tile ----------------------------------
+  const int item0 = blockIdx.x * p.tiles_per_cta;
+  const int ntiles = min(p.tiles_per_cta, p.total_tiles - item0);
+
+  if (warp == 0 && lane == 0) {
+    tc::prefetch_tmap(&p.tmQ); tc::prefetch_tmap(&p.tmKV); tc::prefetch_tmap(&p.tmO);
+    tc::mbar_init(smem_u32(&bar_kv), 1);
+    tc::mbar_init(smem_u32(&kv_empty), 1);
+    tc::mbar_init(smem_u32(&q_full[0]), 1); tc::mbar_init(smem_u32(&q_full[1]), 1);
+    tc::mbar_init(smem_u32(&q_empty[0]), 1); tc::mbar_init(smem_u32(&q_empty[1]), 1);
+    tc::mbar_init(smem_u32(&s_full), 1);
+    tc::mbar_init(smem_u32(&p_ready), 4);
+    tc::mbar_init(smem_u32(&o_full), 1);
+    tc::mbar_init(smem_u32(&tmem_free), 4);
+    tc::fence_mbar_init();
+  }
+  if (warp == 1) tc::tmem_alloc(smem_u32(&tmem_slot), kTmemCols);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    int cur_bh = -1, kv_loads = 0;
+    for (int t = 0; t < ntiles; ++t) {
+      const int item = item0 + t;
+      const int bh = item / p.tiles_per_bh, tile = item - bh * p.tiles_per_bh;
+      const int b = bh / p.H, h = bh - b * p.H;
+      if (bh != cur_bh) {   // new (batch, head): K|V buffer must have been released by the last P V that read it
+        if (kv_loads > 0) tc::mbar_wait(smem_u32(&kv_empty), (uint32_t)(kv_loads - 1) & 1u);
+        if (tc::elect_one()) {
+          const uint32_t bk = smem_u32(&bar_kv);
+          tc::mbar_expect_tx(bk, 2 * kKVBytes);
+          tc::tma_load_3d(smem + kOffK, &p.tmKV, bk, h * kD, 0, b);
+          tc::tma_load_3d(smem + kOffV, &p.tmKV, bk, p.C + h * kD, 0, b);
+        }
+        __syncwarp();
+        cur_bh = bh;
+        ++kv_loads;
+      }
+      const int s = t & 1;
+      tc::mbar_wait(smem_u32(&q_empty[s]), ((uint32_t)(t >> 1) & 1u) ^ 1u);
+      if (tc::elect_one()) {
+        const uint32_t fb = smem_u32(&q_full[s]);
+        tc::mbar_expect_tx(fb, kQBytes);
+        tc::tma_load_3d(smem + (s ? kOffQ1 : kOffQ0), &p.tmQ, fb, h * kD, tile * kQT, b);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    // K-major tiles (Q, K): 128-byte rows, 8-row groups 1024 B apart; K=16 step = 32 B inside the swizzle atom.
+    // MN-major tile (V as B of P V): [key][d], 16 keys per K step = 2048 B.
+    constexpr uint64_t kDescK = ((uint64_t)1 << 16) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
+    constexpr uint64_t kDescMN = ((uint64_t)(8192u >> 4) << 16) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
+    int cur_bh = -1, kv_loads = 0;
+    for (int t = 0; t < ntiles; ++t) {
+      const int s = t & 1;
+      const int bh = (item0 + t) / p.tiles_per_bh;
+      const bool last_of_bh = (t + 1 < ntiles) && ((item0 + t + 1) / p.tiles_per_bh != bh);
+      if (bh != cur_bh) {
+        tc::mbar_wait(smem_u32(&bar_kv), (uint32_t)kv_loads & 1u);
+        cur_bh = bh;
+        ++kv_loads;
+      }
+      tc::mbar_wait(smem_u32(&q_full[s]), (uint32_t)(t >> 1) & 1u);
+      if (t > 0) tc::mbar_wait(smem_u32(&tmem_free), (uint32_t)(t - 1) & 1u);  // O of the previous tile has been read out
+      tc::fence_after_sync();
+      if (tc::elect_one()) {
+        const uint32_t qa = (smem + (s ? kOffQ1 : kOffQ0)) >> 4, ka = (smem + kOffK) >> 4;
+#pragma unroll
+        for (int k = 0; k < kD / 16; ++k)
+          tc::mma_f16_ss(tmem, kDescK | (uint64_t)(qa + k * 2), kDescK | (uint64_t)(ka + k * 2), p.idesc_s, k > 0);
+        tc::mma_commit(smem_u32(&s_full));
+        tc::mma_commit(smem_u32(&q_empty[s]));
+      }
+      __syncwarp();
+      tc::mbar_wait(smem_u32(&p_ready), (uint32_t)t & 1u);
+      tc::fence_after_sync();
+      if (tc::elect_one()) {
+        const uint32_t va = (smem + kOffV) >> 4;
+#pragma unroll
+        for (int k = 0; k < kLP / 16; ++k)  // A = P from TMEM (8 packed columns per K=16 step), B = V
+          tc::mma_f16_ts(tmem + 64, tmem + k * 8, kDescMN | (uint64_t)(va + k * 128), p.idesc_o, k > 0);
+        tc::mma_commit(smem_u32(&o_full));
+        if (last_of_bh) tc::mma_commit(smem_u32(&kv_empty));   // K|V buffer reusable once these MMAs have read it
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===== softmax + epilogue: warp w owns TMEM lanes [32*(w%4), +32); thread = query row =====
+    const int q = warp & 3;
+    const int row = q * 32 + lane;                       // row inside the tile
+    const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16);
+    const uint32_t o_stage = smem + kOffO;
+    const int L = p.L;
+    const float sl2 = p.scale_log2;
+    for (int t = 0; t < ntiles; ++t) {
+      const int item = item0 + t;
+      const int bh = item / p.tiles_per_bh, tile = item - bh * p.tiles_per_bh;
+      const int b = bh / p.H, h = bh - b * p.H;
+      tc::mbar_wait(smem_u32(&s_full), (uint32_t)t & 1u);
+      tc::fence_after_sync();
+      uint32_t sv[kLP];
+      {
+        uint32_t(&c0)[16] = *reinterpret_cast<uint32_t(*)[16]>(&sv[0]);
+        uint32_t(&c1)[16] = *reinterpret_cast<uint32_t(*)[16]>(&sv[16]);
+        uint32_t(&c2)[16] = *reinterpret_cast<uint32_t(*)[16]>(&sv[32]);
+        uint32_t(&c3)[16] = *reinterpret_cast<uint32_t(*)[16]>(&sv[48]);
+        uint32_t(&c4)[16] = *reinterpret_cast<uint32_t(*)[16]>(&sv[64]);
+        tc::tmem_ld16(t_lane + 0, c0); tc::tmem_ld16(t_lane + 16, c1); tc::tmem_ld16(t_lane + 32, c2);
+        tc::tmem_ld16(t_lane + 48, c3); tc::tmem_ld16(t_lane + 64, c4);
+        tc::tmem_ld_wait();
+      }
+      // columns [0, Lfull) need no masking (Lfull = L rounded down to 16: warp-uniform branches below)
+      float m = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < kLP / 16; ++c) {
+        if ((c + 1) * 16 <= L) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) m = fmaxf(m, __uint_as_float(sv[c * 16 + j]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) m = fmaxf(m, c * 16 + j < L ? __uint_as_float(sv[c * 16 + j]) : -INFINITY);
+        }
+      }
+      const float off = m * sl2;
+      float sum = 0.f;
+#pragma unroll
+      for (int c = 0; c < kLP / 16; ++c) {
+        uint32_t pk[8];
+        if ((c + 1) * 16 <= L) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float e0 = ex2(fmaf(__uint_as_float(sv[c * 16 + 2 * j]), sl2, -off));
+            const float e1 = ex2(fmaf(__uint_as_float(sv[c * 16 + 2 * j + 1]), sl2, -off));
+            sum += e0 + e1;
+            pk[j] = pack2<T>(e0, e1);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int j0 = c * 16 + 2 * j;
+            const float e0 = j0 < L ? ex2(fmaf(__uint_as_float(sv[j0]), sl2, -off)) : 0.f;
+            const float e1 = j0 + 1 < L ? ex2(fmaf(__uint_as_float(sv[j0 + 1]), sl2, -off)) : 0.f;
+            sum += e0 + e1;
+            pk[j] = pack2<T>(e0, e1);
+          }
+        }
+        tmem_st8(t_lane + c * 8, pk);   // P (16-bit pairs) over S's own columns: this thread's row only
+      }
+      tc::tmem_st_wait();
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(smem_u32(&p_ready));
+      const float inv = 1.0f / sum;
+
+      // staging tile free again? (the previous tile's TMA store must have finished READING it)
+      if (t > 0) {
+        if (threadIdx.x == 64) tc::tma_store_wait_read<0>();
+        named_bar_sync(1, 128);
+      }
+      tc::mbar_wait(smem_u32(&o_full), (uint32_t)t & 1u);
+      tc::fence_after_sync();
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t ov[32];
+        tc::tmem_ld32(t_lane + 64 + half * 32, ov);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint4 u;
+          u.x = pack2<T>(__uint_as_float(ov[c * 8 + 0]) * inv, __uint_as_float(ov[c * 8 + 1]) * inv);
+          u.y = pack2<T>(__uint_as_float(ov[c * 8 + 2]) * inv, __uint_as_float(ov[c * 8 + 3]) * inv);
+          u.z = pack2<T>(__uint_as_float(ov[c * 8 + 4]) * inv, __uint_as_float(ov[c * 8 + 5]) * inv);
+          u.w = pack2<T>(__uint_as_float(ov[c * 8 + 6]) * inv, __uint_as_float(ov[c * 8 + 7]) * inv);
+          const int chunk = half * 4 + c;  // 16-byte chunk of the 128-byte row; TMA SWIZZLE_128B: chunk ^= row % 8
+          const uint32_t addr = o_stage + (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4);
+          asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w) : "memory");
+        }
+      }
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(smem_u32(&tmem_free));   // S / P / O columns may be overwritten by the next tile
+      tc::fence_proxy_async_smem();                           // generic-proxy smem writes -> visible to the TMA engine
+      named_bar_sync(1, 128);
+      if (threadIdx.x == 64) {
+        tc::tma_store_3d(&p.tmO, o_stage, h * kD, tile * kQT, b);
+        tc::tma_store_commit();
+      }
+    }
+    if (threadIdx.x == 64) tc::tma_store_wait<0>();
+  }
+
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc::fence_after_sync();
+    tc::tmem_dealloc(tmem, kTmemCols);
+  }
+}
+
+template <typename T>
+int launch_fwd_tc(const FwdParams& p, int units, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    PEA_CUDA(cudaFuncSetAttribute(attn2_fwd_tc_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    attr_set = true;
+  }
+  attn2_fwd_tc_kernel<T><<<units, kThreads, kSmemBytes, st>>>(p);
+  PEA_LAUNCH_CHECK();
+  return PEA_OK;
+}
+
+}  // namespace
+
+// Called by pea_attn2_fwd (attn2_mma.cu) when head_dim == 64 and the layout fits TMA (16-byte strides).
+int attn2_fwd_tc(const pea_attn2_desc* a, cudaStream_t st) {
+  FwdParams p{};
+  const bool fp16 = a->dtype == PEA_F16;
+  const int C = a->H * a->d;
+  p.B = a->B; p.N = a->N; p.L = a->L; p.H = a->H; p.C = C;
+  p.scale_log2 = a->scale * 1.4426950408889634f;
+  {
+    const uint64_t dims[3] = {(uint64_t)C, (uint64_t)a->N, (uint64_t)a->B};
+    const uint64_t str[2] = {(uint64_t)a->ld_q * 2, (uint64_t)a->ld_q * 2 * (uint64_t)a->N};
+    const uint32_t box[3] = {64, 128, 1};
+    int rc = encode_tmap_16bit(&p.tmQ, a->d_q, 3, dims, str, box, fp16);
+    if (rc != PEA_OK) return rc;
+    const uint64_t ostr[2] = {(uint64_t)a->ld_o * 2, (uint64_t)a->ld_o * 2 * (uint64_t)a->N};
+    rc = encode_tmap_16bit(&p.tmO, a->d_o, 3, dims, ostr, box, fp16);
+    if (rc != PEA_OK) return rc;
+  }
+  {
+    // K and V share one map: V = K's base + (d_v - d_k) elements along the row (the K|V interleaved layout)
+    const long long voff = (static_cast<const char*>(a->d_v) - static_cast<const char*>(a->d_k)) / 2;
+    const uint64_t dims[3] = {(uint64_t)(voff + C), (uint64_t)a->L, (uint64_t)a->B};
+    const uint64_t str[2] = {(uint64_t)a->ld_kv * 2, (uint64_t)a->bs_kv * 2};
+    const uint32_t box[3] = {64, (uint32_t)kLP, 1};
+    int rc = encode_tmap_16bit(&p.tmKV, a->d_k, 3, dims, str, box, fp16);
+    if (rc != PEA_OK) return rc;
+    p.C = (int)voff;  // column offset of V inside the shared map
+  }
+  p.tiles_per_bh = (a->N + kQT - 1) / kQT;
+  p.total_tiles = a->B * a->H * p.tiles_per_bh;
+  // <= 3 resident CTAs per SM, each with a contiguous range of work items
+  const int slots = num_sms() * 3;
+  p.tiles_per_cta = (p.total_tiles + slots - 1) / slots;
+  const int units = (p.total_tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
+  p.idesc_s = tc::make_idesc(fp16 ? 0 : 1, 128, kLP, 0, 0);
+  p.idesc_o = tc::make_idesc(fp16 ? 0 : 1, 128, kD, 0, 1);
+  return fp16 ? launch_fwd_tc<__half>(p, units, st) : launch_fwd_tc<__nv_bfloat16>(p, units, st);
+}
+
+bool attn2_fwd_tc_eligible(const pea_attn2_desc* a) {
+  if (a->d != kD || a->L > kLP) return false;
+  const long long voff = (static_cast<const char*>(a->d_v) - static_cast<const char*>(a->d_k)) / 2;
+  const int C = a->H * a->d;
+  // K|V interleaved in one [B, L, *] tensor with V to the right of K inside the row, 16-byte aligned everything
+  return voff >= C && voff + C <= a->ld_kv && a->ld_q % 8 == 0 && a->ld_o % 8 == 0 && a->ld_kv % 8 == 0 && a->bs_kv % 8 == 0 &&
+         (reinterpret_cast<uintptr_t>(a->d_q) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->d_k) & 15) == 0 &&
+         (reinterpret_cast<uintptr_t>(a->d_o) & 15) == 0 && voff % 8 == 0;
+}
+
+}  // namespace pea
