@@ -2,21 +2,23 @@
 //
 // Replaces F.scaled_dot_product_attention inside diffusers' AttnProcessor2_0 (reached from train_sdxl_zh.py:397,415 and
 // tests/test_sdxl_zh.py:384-391) for the <= 80-key regime.  HBM-bound: Q streams in once, O streams out once; the
-// projected context K|V of one (batch, head) -- 2 x 80 x 64 x 2 B = 20 KiB -- is TMA'd into shared memory once per CTA.
+// projected context K|V of one (batch, head) -- 2 x 80 x 64 x 2 B = 20 KiB -- stays in shared memory while the CTA
+// walks that head's query tiles.
 //
-// Persistent-style grid: <= 3 CTAs per SM, each CTA walks a CONTIGUOUS range of (batch, head, 128-row query tile) work
-// items (query tile fastest), so Q prefetch never drains and K|V is reloaded only when (batch, head) changes.
-// 192 threads per CTA:
-//   warp 0      TMA producer: K, V tiles (rows >= L zero-filled by TMA) on a (batch, head) change, Q tiles into a
-//               2-deep ring
-//   warp 1      TMEM allocator + MMA issuer:  S = Q K^T   (tcgen05.mma SS, M128 N80 K64  -> TMEM cols [0,80))
-//                                             O = P V     (tcgen05.mma TS, M128 N64 K80  -> TMEM cols [64,128))
-//   warps 2..5  softmax + epilogue, thread = query row (TMEM lane): tcgen05.ld S, single-pass softmax (all keys are in
-//               the tile: no online rescaling, no cross-thread reduction at all), unnormalised P -> bf16 -> tcgen05.st
-//               over S's own columns [0,40), later tcgen05.ld O, scale by 1/rowsum, 128B-swizzled staging tile,
-//               TMA store (clips the N tail).
-// TMEM: 128 columns per CTA (S [0,80) aliased by P [0,40); O [64,128) is only written after S is dead).
-// Algorithmic bytes per CTA tile: 128 x 64 x 2 B in + the same out; FLOPs 4 x 128 x 80 x 64.
+// Persistent grid: one CTA per SM, each walking a CONTIGUOUS range of (batch, head, 128-row query tile) work items
+// (query tile fastest), so the Q ring never drains and K|V is reloaded only when (batch, head) changes (double
+// buffered, prefetched).  320 threads:
+//   warp 0      TMA producer: K|V tiles (rows >= L zero-filled by TMA), Q tiles into a 4-deep ring
+//   warp 1      TMEM allocator + MMA issuer, software pipelined  S(t+1) = Q K^T  ahead of  O(t) = P V:
+//                 S = Q K^T   tcgen05.mma SS, M128 N80 K64  -> TMEM S[t&1]
+//                 O = P V     tcgen05.mma TS, M128 N64 K80  -> TMEM O[t&1]   (A = P straight from TMEM)
+//   warps 2..5  softmax/epilogue group 0 (even tiles), warps 6..9 group 1 (odd tiles); thread = query row = TMEM lane:
+//               tcgen05.ld S, single-pass softmax (all keys are in the tile: no online rescaling and no cross-thread
+//               reduction), unnormalised P -> 16-bit -> tcgen05.st over S's own columns, later tcgen05.ld O, scale by
+//               1/rowsum, 128B-swizzled staging tile, TMA store (clips the N tail).
+// While group 0 runs the softmax of tile t the tensor core already computes S(t+1) for group 1, and the TMA engine is
+// up to four Q tiles ahead.  TMEM: 512 columns (S/P x2, O x2).
+// Algorithmic bytes per tile: 128 x 64 x 2 B in + the same out; FLOPs 4 x 128 x 80 x 64.
 #include "tc05.cuh"
 
 namespace pea {
@@ -25,12 +27,16 @@ namespace {
 constexpr int kQT = 128;                 // query rows per tile
 constexpr int kD = 64;                   // head dim
 constexpr int kLP = 80;                  // padded key count
-constexpr int kThreads = 192;
-constexpr uint32_t kTmemCols = 128;
+constexpr int kQStages = 4;
+constexpr int kThreads = 320;
+constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kTmemS = 0, kTmemSStride = 128, kTmemO = 256, kTmemOStride = 64;
 constexpr uint32_t kQBytes = kQT * kD * 2;      // 16 KiB
-constexpr uint32_t kKVBytes = kLP * kD * 2;     // 10 KiB each
-constexpr uint32_t kOffK = 0, kOffV = 10240, kOffQ0 = 20480, kOffQ1 = kOffQ0 + kQBytes, kOffO = kOffQ1 + kQBytes;
-constexpr uint32_t kSmemBytes = kOffO + kQBytes + 1024;  // + alignment slack
+constexpr uint32_t kKVBytes = kLP * kD * 2;     // 10 KiB each (K, V)
+constexpr uint32_t kOffKV = 0;                                 // 2 buffers x (K 10 KiB | V 10 KiB)
+constexpr uint32_t kOffQ = 2 * 2 * kKVBytes;                   // 4-deep ring
+constexpr uint32_t kOffO = kOffQ + kQStages * kQBytes;         // one staging tile per softmax group
+constexpr uint32_t kSmemBytes = kOffO + 2 * kQBytes + 1024;    // + alignment slack
 
 struct FwdParams {
   CUtensorMap tmQ, tmKV, tmO;
@@ -53,9 +59,10 @@ __device__ __forceinline__ float ex2(float x) {
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
 template <typename T>
-__global__ void __launch_bounds__(kThreads, 3) attn2_fwd_tc_kernel(const __grid_constant__ FwdParams p) {
+__global__ void __launch_bounds__(kThreads, 1) attn2_fwd_tc_kernel(const __grid_constant__ FwdParams p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bar_kv, kv_empty, q_full[2], q_empty[2], s_full, p_ready, o_full, tmem_free;
+  __shared__ __align__(8) uint64_t kv_full[2], kv_empty[2], q_full[kQStages], q_empty[kQStages];
+  __shared__ __align__(8) uint64_t s_full[2], p_ready[2], o_full[2], tmem_free[2];
   __shared__ uint32_t tmem_slot;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -64,17 +71,18 @@ __global__ void __launch_bounds__(kThreads, 3) attn2_fwd_tc_kernel(const __grid_
   // ---- this CTA's contiguous range of work items; item = bh * tiles_per_bh + tile ----------------------------------
   const int item0 = blockIdx.x * p.tiles_per_cta;
   const int ntiles = min(p.tiles_per_cta, p.total_tiles - item0);
+  const int tpb = p.tiles_per_bh;
 
   if (warp == 0 && lane == 0) {
     tc::prefetch_tmap(&p.tmQ); tc::prefetch_tmap(&p.tmKV); tc::prefetch_tmap(&p.tmO);
-    tc::mbar_init(smem_u32(&bar_kv), 1);
-    tc::mbar_init(smem_u32(&kv_empty), 1);
-    tc::mbar_init(smem_u32(&q_full[0]), 1); tc::mbar_init(smem_u32(&q_full[1]), 1);
-    tc::mbar_init(smem_u32(&q_empty[0]), 1); tc::mbar_init(smem_u32(&q_empty[1]), 1);
-    tc::mbar_init(smem_u32(&s_full), 1);
-    tc::mbar_init(smem_u32(&p_ready), 4);
-    tc::mbar_init(smem_u32(&o_full), 1);
-    tc::mbar_init(smem_u32(&tmem_free), 4);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      tc::mbar_init(smem_u32(&kv_full[i]), 1); tc::mbar_init(smem_u32(&kv_empty[i]), 1);
+      tc::mbar_init(smem_u32(&s_full[i]), 1); tc::mbar_init(smem_u32(&p_ready[i]), 4);
+      tc::mbar_init(smem_u32(&o_full[i]), 1); tc::mbar_init(smem_u32(&tmem_free[i]), 4);
+    }
+#pragma unroll
+    for (int i = 0; i < kQStages; ++i) { tc::mbar_init(smem_u32(&q_full[i]), 1); tc::mbar_init(smem_u32(&q_empty[i]), 1); }
     tc::fence_mbar_init();
   }
   if (warp == 1) tc::tmem_alloc(smem_u32(&tmem_slot), kTmemCols);
@@ -85,29 +93,30 @@ __global__ void __launch_bounds__(kThreads, 3) attn2_fwd_tc_kernel(const __grid_
 
   if (warp == 0) {
     // ===== TMA producer =====
-    int cur_bh = -1, kv_loads = 0;
+    int cur_bh = -1, kv_n = 0;
     for (int t = 0; t < ntiles; ++t) {
       const int item = item0 + t;
-      const int bh = item / p.tiles_per_bh, tile = item - bh * p.tiles_per_bh;
+      const int bh = item / tpb, tile = item - bh * tpb;
       const int b = bh / p.H, h = bh - b * p.H;
-      if (bh != cur_bh) {   // new (batch, head): K|V buffer must have been released by the last P V that read it
-        if (kv_loads > 0) tc::mbar_wait(smem_u32(&kv_empty), (uint32_t)(kv_loads - 1) & 1u);
+      if (bh != cur_bh) {   // new (batch, head): next K|V buffer (freed by the last P V that read it two loads ago)
+        const int kb = kv_n & 1;
+        tc::mbar_wait(smem_u32(&kv_empty[kb]), ((uint32_t)(kv_n >> 1) & 1u) ^ 1u);
         if (tc::elect_one()) {
-          const uint32_t bk = smem_u32(&bar_kv);
+          const uint32_t bk = smem_u32(&kv_full[kb]);
           tc::mbar_expect_tx(bk, 2 * kKVBytes);
-          tc::tma_load_3d(smem + kOffK, &p.tmKV, bk, h * kD, 0, b);
-          tc::tma_load_3d(smem + kOffV, &p.tmKV, bk, p.C + h * kD, 0, b);
+          tc::tma_load_3d(smem + kOffKV + kb * 2 * kKVBytes, &p.tmKV, bk, h * kD, 0, b);
+          tc::tma_load_3d(smem + kOffKV + kb * 2 * kKVBytes + kKVBytes, &p.tmKV, bk, p.C + h * kD, 0, b);
         }
         __syncwarp();
         cur_bh = bh;
-        ++kv_loads;
+        ++kv_n;
       }
-      const int s = t & 1;
-      tc::mbar_wait(smem_u32(&q_empty[s]), ((uint32_t)(t >> 1) & 1u) ^ 1u);
+      const int s = t % kQStages;
+      tc::mbar_wait(smem_u32(&q_empty[s]), ((uint32_t)(t / kQStages) & 1u) ^ 1u);
       if (tc::elect_one()) {
         const uint32_t fb = smem_u32(&q_full[s]);
         tc::mbar_expect_tx(fb, kQBytes);
-        tc::tma_load_3d(smem + (s ? kOffQ1 : kOffQ0), &p.tmQ, fb, h * kD, tile * kQT, b);
+        tc::tma_load_3d(smem + kOffQ + s * kQBytes, &p.tmQ, fb, h * kD, tile * kQT, b);
       }
       __syncwarp();
     }
@@ -117,53 +126,66 @@ __global__ void __launch_bounds__(kThreads, 3) attn2_fwd_tc_kernel(const __grid_
     // MN-major tile (V as B of P V): [key][d], 16 keys per K step = 2048 B.
     constexpr uint64_t kDescK = ((uint64_t)1 << 16) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
     constexpr uint64_t kDescMN = ((uint64_t)(8192u >> 4) << 16) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
-    int cur_bh = -1, kv_loads = 0;
-    for (int t = 0; t < ntiles; ++t) {
-      const int s = t & 1;
-      const int bh = (item0 + t) / p.tiles_per_bh;
-      const bool last_of_bh = (t + 1 < ntiles) && ((item0 + t + 1) / p.tiles_per_bh != bh);
-      if (bh != cur_bh) {
-        tc::mbar_wait(smem_u32(&bar_kv), (uint32_t)kv_loads & 1u);
-        cur_bh = bh;
-        ++kv_loads;
+    int s_bh = -1, s_kvn = 0;       // K|V bookkeeping of the S stream (runs one tile ahead of the P V stream)
+    int o_bh = -1, o_kvn = 0;
+    auto issue_s = [&](int t) {
+      const int bh = (item0 + t) / tpb;
+      if (bh != s_bh) {
+        tc::mbar_wait(smem_u32(&kv_full[s_kvn & 1]), (uint32_t)(s_kvn >> 1) & 1u);
+        s_bh = bh;
+        ++s_kvn;
       }
-      tc::mbar_wait(smem_u32(&q_full[s]), (uint32_t)(t >> 1) & 1u);
-      if (t > 0) tc::mbar_wait(smem_u32(&tmem_free), (uint32_t)(t - 1) & 1u);  // O of the previous tile has been read out
+      const int kb = (s_kvn - 1) & 1, qs = t % kQStages, j = t & 1;
+      tc::mbar_wait(smem_u32(&q_full[qs]), (uint32_t)(t / kQStages) & 1u);
+      if (t >= 2) tc::mbar_wait(smem_u32(&tmem_free[j]), (uint32_t)((t >> 1) - 1) & 1u);  // S/P/O[j] of tile t-2 drained
       tc::fence_after_sync();
       if (tc::elect_one()) {
-        const uint32_t qa = (smem + (s ? kOffQ1 : kOffQ0)) >> 4, ka = (smem + kOffK) >> 4;
+        const uint32_t qa = (smem + kOffQ + qs * kQBytes) >> 4, ka = (smem + kOffKV + kb * 2 * kKVBytes) >> 4;
 #pragma unroll
         for (int k = 0; k < kD / 16; ++k)
-          tc::mma_f16_ss(tmem, kDescK | (uint64_t)(qa + k * 2), kDescK | (uint64_t)(ka + k * 2), p.idesc_s, k > 0);
-        tc::mma_commit(smem_u32(&s_full));
-        tc::mma_commit(smem_u32(&q_empty[s]));
+          tc::mma_f16_ss(tmem + kTmemS + j * kTmemSStride, kDescK | (uint64_t)(qa + k * 2), kDescK | (uint64_t)(ka + k * 2), p.idesc_s, k > 0);
+        tc::mma_commit(smem_u32(&s_full[j]));
+        tc::mma_commit(smem_u32(&q_empty[qs]));
       }
       __syncwarp();
-      tc::mbar_wait(smem_u32(&p_ready), (uint32_t)t & 1u);
+    };
+    if (ntiles > 0) issue_s(0);
+    for (int t = 0; t < ntiles; ++t) {
+      if (t + 1 < ntiles) issue_s(t + 1);
+      const int bh = (item0 + t) / tpb, j = t & 1;
+      if (bh != o_bh) { o_bh = bh; ++o_kvn; }
+      const int kb = (o_kvn - 1) & 1;
+      const bool last_of_bh = (t + 1 < ntiles) && ((item0 + t + 1) / tpb != bh);
+      tc::mbar_wait(smem_u32(&p_ready[j]), (uint32_t)(t >> 1) & 1u);
       tc::fence_after_sync();
       if (tc::elect_one()) {
-        const uint32_t va = (smem + kOffV) >> 4;
+        const uint32_t va = (smem + kOffKV + kb * 2 * kKVBytes + kKVBytes) >> 4;
+        const uint32_t tp = tmem + kTmemS + j * kTmemSStride, to = tmem + kTmemO + j * kTmemOStride;
 #pragma unroll
         for (int k = 0; k < kLP / 16; ++k)  // A = P from TMEM (8 packed columns per K=16 step), B = V
-          tc::mma_f16_ts(tmem + 64, tmem + k * 8, kDescMN | (uint64_t)(va + k * 128), p.idesc_o, k > 0);
-        tc::mma_commit(smem_u32(&o_full));
-        if (last_of_bh) tc::mma_commit(smem_u32(&kv_empty));   // K|V buffer reusable once these MMAs have read it
+          tc::mma_f16_ts(to, tp + k * 8, kDescMN | (uint64_t)(va + k * 128), p.idesc_o, k > 0);
+        tc::mma_commit(smem_u32(&o_full[j]));
+        if (last_of_bh) tc::mma_commit(smem_u32(&kv_empty[kb]));   // K|V buffer reusable once these MMAs have read it
       }
       __syncwarp();
     }
   } else {
-    // ===== softmax + epilogue: warp w owns TMEM lanes [32*(w%4), +32); thread = query row =====
+    // ===== softmax + epilogue groups: warp w owns TMEM lanes [32*(w%4), +32); thread = query row =====
+    const int g = (warp - 2) >> 2;                       // group 0: warps 2..5 (even tiles), group 1: warps 6..9 (odd tiles)
     const int q = warp & 3;
     const int row = q * 32 + lane;                       // row inside the tile
-    const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16);
-    const uint32_t o_stage = smem + kOffO;
+    const uint32_t t_s = tmem + kTmemS + g * kTmemSStride + ((uint32_t)(q * 32) << 16);
+    const uint32_t t_o = tmem + kTmemO + g * kTmemOStride + ((uint32_t)(q * 32) << 16);
+    const uint32_t o_stage = smem + kOffO + g * kQBytes;
+    const bool issuer = threadIdx.x == 64 + g * 128;
     const int L = p.L;
     const float sl2 = p.scale_log2;
-    for (int t = 0; t < ntiles; ++t) {
+    for (int t = g; t < ntiles; t += 2) {
+      const uint32_t ph = (uint32_t)(t >> 1) & 1u;
       const int item = item0 + t;
-      const int bh = item / p.tiles_per_bh, tile = item - bh * p.tiles_per_bh;
+      const int bh = item / tpb, tile = item - bh * tpb;
       const int b = bh / p.H, h = bh - b * p.H;
-      tc::mbar_wait(smem_u32(&s_full), (uint32_t)t & 1u);
+      tc::mbar_wait(smem_u32(&s_full[g]), ph);
       tc::fence_after_sync();
       uint32_t sv[kLP];
       {
@@ -172,8 +194,8 @@ __global__ void __launch_bounds__(kThreads, 3) attn2_fwd_tc_kernel(const __grid_
         uint32_t(&c2)[16] = *reinterpret_cast<uint32_t(*)[16]>(&sv[32]);
         uint32_t(&c3)[16] = *reinterpret_cast<uint32_t(*)[16]>(&sv[48]);
         uint32_t(&c4)[16] = *reinterpret_cast<uint32_t(*)[16]>(&sv[64]);
-        tc::tmem_ld16(t_lane + 0, c0); tc::tmem_ld16(t_lane + 16, c1); tc::tmem_ld16(t_lane + 32, c2);
-        tc::tmem_ld16(t_lane + 48, c3); tc::tmem_ld16(t_lane + 64, c4);
+        tc::tmem_ld16(t_s + 0, c0); tc::tmem_ld16(t_s + 16, c1); tc::tmem_ld16(t_s + 32, c2);
+        tc::tmem_ld16(t_s + 48, c3); tc::tmem_ld16(t_s + 64, c4);
         tc::tmem_ld_wait();
       }
       // columns [0, Lfull) need no masking (Lfull = L rounded down to 16: warp-uniform branches below)
@@ -211,25 +233,25 @@ __global__ void __launch_bounds__(kThreads, 3) attn2_fwd_tc_kernel(const __grid_
             pk[j] = pack2<T>(e0, e1);
           }
         }
-        tmem_st8(t_lane + c * 8, pk);   // P (16-bit pairs) over S's own columns: this thread's row only
+        tmem_st8(t_s + c * 8, pk);   // P (16-bit pairs) over S's own columns: this thread's row only
       }
       tc::tmem_st_wait();
       tc::fence_before_sync();
       __syncwarp();
-      if (lane == 0) tc::mbar_arrive(smem_u32(&p_ready));
+      if (lane == 0) tc::mbar_arrive(smem_u32(&p_ready[g]));
       const float inv = 1.0f / sum;
 
-      // staging tile free again? (the previous tile's TMA store must have finished READING it)
-      if (t > 0) {
-        if (threadIdx.x == 64) tc::tma_store_wait_read<0>();
-        named_bar_sync(1, 128);
+      // staging tile free again? (this group's previous TMA store must have finished READING it)
+      if (t >= 2) {
+        if (issuer) tc::tma_store_wait_read<0>();
+        named_bar_sync(1 + g, 128);
       }
-      tc::mbar_wait(smem_u32(&o_full), (uint32_t)t & 1u);
+      tc::mbar_wait(smem_u32(&o_full[g]), ph);
       tc::fence_after_sync();
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         uint32_t ov[32];
-        tc::tmem_ld32(t_lane + 64 + half * 32, ov);
+        tc::tmem_ld32(t_o + half * 32, ov);
         tc::tmem_ld_wait();
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
@@ -245,15 +267,15 @@ __global__ void __launch_bounds__(kThreads, 3) attn2_fwd_tc_kernel(const __grid_
       }
       tc::fence_before_sync();
       __syncwarp();
-      if (lane == 0) tc::mbar_arrive(smem_u32(&tmem_free));   // S / P / O columns may be overwritten by the next tile
-      tc::fence_proxy_async_smem();                           // generic-proxy smem writes -> visible to the TMA engine
-      named_bar_sync(1, 128);
-      if (threadIdx.x == 64) {
+      if (lane == 0) tc::mbar_arrive(smem_u32(&tmem_free[g]));   // S / P / O[g] may be overwritten by tile t + 2
+      tc::fence_proxy_async_smem();                              // generic-proxy smem writes -> visible to the TMA engine
+      named_bar_sync(1 + g, 128);
+      if (issuer) {
         tc::tma_store_3d(&p.tmO, o_stage, h * kD, tile * kQT, b);
         tc::tma_store_commit();
       }
     }
-    if (threadIdx.x == 64) tc::tma_store_wait<0>();
+    if (issuer) tc::tma_store_wait<0>();
   }
 
   tc::fence_before_sync();
@@ -307,8 +329,8 @@ int attn2_fwd_tc(const pea_attn2_desc* a, cudaStream_t st) {
   }
   p.tiles_per_bh = (a->N + kQT - 1) / kQT;
   p.total_tiles = a->B * a->H * p.tiles_per_bh;
-  // <= 3 resident CTAs per SM, each with a contiguous range of work items
-  const int slots = num_sms() * 3;
+  // one persistent CTA per SM, each with a contiguous range of work items
+  const int slots = num_sms();
   p.tiles_per_cta = (p.total_tiles + slots - 1) / slots;
   const int units = (p.total_tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
   p.idesc_s = tc::make_idesc(fp16 ? 0 : 1, 128, kLP, 0, 0);
