@@ -1,0 +1,454 @@
+// attn2_bwd_tc.cu -- tcgen05 / TMEM / TMA backward of the fused cross-attention core for head_dim 64.
+//
+// Gradient of softmax(q k^T scale) v as autograd forms it for diffusers' AttnProcessor2_0 under train_sdxl_zh.py:397
+// (student UNet; DeepSpeed backward) -- dQ, and dK / dV which the caller turns into dContext.  Because all <= 80 keys
+// sit in one tile, S and P are RECOMPUTED from Q, K and delta = rowsum(P o dP) is local to a query row, so neither O
+// nor a log-sum-exp is read: HBM traffic is read Q, read dO, write dQ (+ the tiny K, V, dK, dV).
+//
+// One persistent CTA per SM walks a contiguous range of (batch, head, 128-row query tile) items.  352 threads:
+//   warp 0       TMA producer: K|V (double buffered, on a (batch, head) change), Q and dO tiles (3-deep ring)
+//   warp 1       TMEM allocator + MMA issuer (all tcgen05.mma, M128, fp32 accumulate):
+//                  S  = Q  K^T      SS  N80  K64   -> S[g]                    (g = tile parity)
+//                  dP = dO V^T      SS  N80  K64   -> dP[g]
+//                  dQ = dS K        TS  N64  K80   -> dQ      (A = dS, 16-bit, straight from TMEM over dP[g])
+//                  dV += P^T  dO    SS  N64  K128  -> dV      (A = P  from smem, MN-major; rows = keys)
+//                  dK += dS^T Q     SS  N64  K128  -> dK      (A = dS from smem, MN-major)
+//                dK / dV accumulate in TMEM across the CTA's consecutive tiles of one (batch, head).
+//   warps 2..5   softmax group 0 (even tiles), warps 6..9 group 1 (odd tiles); thread = query row = TMEM lane:
+//                P = softmax(S), delta, dS = P o (dP - delta) * scale; P, dS -> shared memory (MN-major, 128B swizzle)
+//                and dS -> TMEM; later dQ TMEM -> 16-bit -> swizzled staging tile; on a (batch, head) change the
+//                group drains dK / dV (lane = key) and adds them to the fp32 accumulators in global memory.
+//   warp 10      dQ TMA-store issuer (so no softmax thread ever blocks on a store).
+// TMEM (512 columns): S[2] | dP[2] (160 each pair), dQ 64, dK 64, dV 64.
+// Algorithmic bytes per tile: 2 x 16 KiB in (Q, dO) + 16 KiB out (dQ); FLOPs 10 x 128 x 80 x 64.
+#include "tc05.cuh"
+
+namespace pea {
+namespace {
+
+constexpr int kQT = 128, kD = 64, kLP = 80;
+constexpr int kRing = 3;
+constexpr int kThreads = 352;
+constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kTS = 0, kTdP = 80, kTPair = 160, kTdQ = 320, kTdK = 384, kTdV = 448;
+constexpr uint32_t kTile = kQT * kD * 2;        // 16 KiB: one Q / dO / dQ tile
+constexpr uint32_t kKV = kLP * kD * 2;          // 10 KiB: K or V
+constexpr uint32_t kSlab = kQT * 128;           // 16 KiB: [128 q][64 keys] slab of P / dS
+constexpr uint32_t kOffKV = 0;                              // 2 x (K | V)
+constexpr uint32_t kOffRing = 2 * 2 * kKV;                  // 3 x (Q | dO)
+constexpr uint32_t kOffP = kOffRing + kRing * 2 * kTile;    // 2 slabs
+constexpr uint32_t kOffdS = kOffP + 2 * kSlab;              // 2 slabs
+constexpr uint32_t kOffStage = kOffdS + 2 * kSlab;          // dQ staging
+constexpr uint32_t kSmemBytes = kOffStage + kTile + 1024;
+
+struct BwdParams {
+  CUtensorMap tmQ, tmdO, tmKV, tmdQ;
+  int B, N, L, H, voff;
+  int tiles_per_bh, total_tiles, tiles_per_cta;
+  float scale_log2, scale;
+  uint32_t idesc_s, idesc_dq, idesc_dkv;
+  float* dk; float* dv; long long ld_dkv, bs_dkv;
+  int vec_atomics;
+};
+
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]),
+               "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ void st_shared16(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads, 1) attn2_bwd_tc_kernel(const __grid_constant__ BwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t kv_full[2], kv_empty[2], ring_full[kRing], ring_empty[kRing];
+  __shared__ __align__(8) uint64_t sdp_full[2], ds_ready[2], pds_free, dq_full, dq_free, dkv_full, dkv_free, dq_staged, stage_free;
+  __shared__ uint32_t tmem_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int item0 = blockIdx.x * p.tiles_per_cta;
+  const int ntiles = min(p.tiles_per_cta, p.total_tiles - item0);
+  const int tpb = p.tiles_per_bh;
+
+  if (warp == 0 && lane == 0) {
+    tc::prefetch_tmap(&p.tmQ); tc::prefetch_tmap(&p.tmdO); tc::prefetch_tmap(&p.tmKV); tc::prefetch_tmap(&p.tmdQ);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      tc::mbar_init(smem_u32(&kv_full[i]), 1); tc::mbar_init(smem_u32(&kv_empty[i]), 1);
+      tc::mbar_init(smem_u32(&sdp_full[i]), 1); tc::mbar_init(smem_u32(&ds_ready[i]), 4);
+    }
+#pragma unroll
+    for (int i = 0; i < kRing; ++i) { tc::mbar_init(smem_u32(&ring_full[i]), 1); tc::mbar_init(smem_u32(&ring_empty[i]), 1); }
+    tc::mbar_init(smem_u32(&pds_free), 1);
+    tc::mbar_init(smem_u32(&dq_full), 1);
+    tc::mbar_init(smem_u32(&dq_free), 4);
+    tc::mbar_init(smem_u32(&dkv_full), 1);
+    tc::mbar_init(smem_u32(&dkv_free), 4);
+    tc::mbar_init(smem_u32(&dq_staged), 4);
+    tc::mbar_init(smem_u32(&stage_free), 1);
+    tc::fence_mbar_init();
+  }
+  if (warp == 1) tc::tmem_alloc(smem_u32(&tmem_slot), kTmemCols);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    int cur_bh = -1, kv_n = 0;
+    for (int t = 0; t < ntiles; ++t) {
+      const int item = item0 + t;
+      const int bh = item / tpb, tile = item - bh * tpb;
+      const int b = bh / p.H, h = bh - b * p.H;
+      if (bh != cur_bh) {
+        const int kb = kv_n & 1;
+        tc::mbar_wait(smem_u32(&kv_empty[kb]), ((uint32_t)(kv_n >> 1) & 1u) ^ 1u);
+        if (tc::elect_one()) {
+          const uint32_t bk = smem_u32(&kv_full[kb]);
+          tc::mbar_expect_tx(bk, 2 * kKV);
+          tc::tma_load_3d(smem + kOffKV + kb * 2 * kKV, &p.tmKV, bk, h * kD, 0, b);
+          tc::tma_load_3d(smem + kOffKV + kb * 2 * kKV + kKV, &p.tmKV, bk, p.voff + h * kD, 0, b);
+        }
+        __syncwarp();
+        cur_bh = bh;
+        ++kv_n;
+      }
+      const int s = t % kRing;
+      tc::mbar_wait(smem_u32(&ring_empty[s]), ((uint32_t)(t / kRing) & 1u) ^ 1u);
+      if (tc::elect_one()) {
+        const uint32_t fb = smem_u32(&ring_full[s]);
+        tc::mbar_expect_tx(fb, 2 * kTile);
+        tc::tma_load_3d(smem + kOffRing + s * 2 * kTile, &p.tmQ, fb, h * kD, tile * kQT, b);
+        tc::tma_load_3d(smem + kOffRing + s * 2 * kTile + kTile, &p.tmdO, fb, h * kD, tile * kQT, b);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    // K-major tiles [rows][64 x 16-bit] (Q, dO as A; K, V as B of S / dP): K=16 step = 32 B inside the swizzle atom.
+    // MN-major tiles: K, Q, dO as B ([k rows][64 contiguous]): K=16 step = 16 rows = 2048 B;
+    //                 P, dS as A ([q rows][keys], two 64-key slabs 16 KiB apart = LBO): K=16 step = 16 q rows = 2048 B.
+    constexpr uint64_t kDescK = ((uint64_t)1 << 16) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
+    constexpr uint64_t kDescMN = ((uint64_t)(kSlab >> 4) << 16) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
+    int s_bh = -1, s_kvn = 0;   // K|V bookkeeping of the S/dP stream (runs up to two tiles ahead)
+    int m_bh = -1, m_kvn = 0;   // ... and of the dQ/dK/dV stream
+    int flushes = 0;
+    auto issue_sdp = [&](int t) {
+      const int bh = (item0 + t) / tpb;
+      if (bh != s_bh) {
+        tc::mbar_wait(smem_u32(&kv_full[s_kvn & 1]), (uint32_t)(s_kvn >> 1) & 1u);
+        s_bh = bh;
+        ++s_kvn;
+      }
+      const int kb = (s_kvn - 1) & 1, rs = t % kRing, g = t & 1;
+      tc::mbar_wait(smem_u32(&ring_full[rs]), (uint32_t)(t / kRing) & 1u);
+      tc::fence_after_sync();
+      if (tc::elect_one()) {
+        const uint32_t qa = (smem + kOffRing + rs * 2 * kTile) >> 4, doa = qa + (kTile >> 4);
+        const uint32_t ka = (smem + kOffKV + kb * 2 * kKV) >> 4, va = ka + (kKV >> 4);
+        const uint32_t ts = tmem + g * kTPair + kTS, tdp = tmem + g * kTPair + kTdP;
+#pragma unroll
+        for (int k = 0; k < kD / 16; ++k)
+          tc::mma_f16_ss(ts, kDescK | (uint64_t)(qa + k * 2), kDescK | (uint64_t)(ka + k * 2), p.idesc_s, k > 0);
+#pragma unroll
+        for (int k = 0; k < kD / 16; ++k)
+          tc::mma_f16_ss(tdp, kDescK | (uint64_t)(doa + k * 2), kDescK | (uint64_t)(va + k * 2), p.idesc_s, k > 0);
+        tc::mma_commit(smem_u32(&sdp_full[g]));
+      }
+      __syncwarp();
+    };
+    if (ntiles > 0) issue_sdp(0);
+    if (ntiles > 1) issue_sdp(1);
+    for (int t = 0; t < ntiles; ++t) {
+      const int bh = (item0 + t) / tpb, g = t & 1, rs = t % kRing;
+      const bool first_of_bh = bh != m_bh;
+      if (first_of_bh) { m_bh = bh; ++m_kvn; }
+      const int kb = (m_kvn - 1) & 1;
+      const bool last_tile = t + 1 == ntiles;
+      const bool last_of_bh = !last_tile && ((item0 + t + 1) / tpb != bh);
+      tc::mbar_wait(smem_u32(&ds_ready[g]), (uint32_t)(t >> 1) & 1u);
+      if (t > 0) tc::mbar_wait(smem_u32(&dq_free), (uint32_t)(t - 1) & 1u);            // dQ TMEM drained by tile t-1's epilogue
+      if (first_of_bh && flushes > 0) tc::mbar_wait(smem_u32(&dkv_free), (uint32_t)(flushes - 1) & 1u);  // dK/dV TMEM drained
+      tc::fence_after_sync();
+      if (tc::elect_one()) {
+        const uint32_t qa = (smem + kOffRing + rs * 2 * kTile) >> 4, doa = qa + (kTile >> 4);
+        const uint32_t ka = (smem + kOffKV + kb * 2 * kKV) >> 4;
+        const uint32_t pa = (smem + kOffP) >> 4, dsa = (smem + kOffdS) >> 4;
+        const uint32_t tds = tmem + g * kTPair + kTdP;
+        // dQ = dS K   (A: 16-bit dS in TMEM, 8 columns per K=16 step; B: K tile read MN-major)
+#pragma unroll
+        for (int k = 0; k < kLP / 16; ++k)
+          tc::mma_f16_ts(tmem + kTdQ, tds + k * 8, kDescMN | (uint64_t)(ka + k * 128), p.idesc_dq, k > 0);
+        tc::mma_commit(smem_u32(&dq_full));
+        // dV += P^T dO ; dK += dS^T Q   (reduction over the 128 query rows)
+#pragma unroll
+        for (int k = 0; k < kQT / 16; ++k)
+          tc::mma_f16_ss(tmem + kTdV, kDescMN | (uint64_t)(pa + k * 128), kDescMN | (uint64_t)(doa + k * 128), p.idesc_dkv,
+                         (k > 0) ? 1u : (uint32_t)!first_of_bh);
+#pragma unroll
+        for (int k = 0; k < kQT / 16; ++k)
+          tc::mma_f16_ss(tmem + kTdK, kDescMN | (uint64_t)(dsa + k * 128), kDescMN | (uint64_t)(qa + k * 128), p.idesc_dkv,
+                         (k > 0) ? 1u : (uint32_t)!first_of_bh);
+        tc::mma_commit(smem_u32(&pds_free));            // P / dS shared-memory tiles reusable
+        tc::mma_commit(smem_u32(&ring_empty[rs]));      // Q / dO slot reusable
+        if (last_of_bh || last_tile) tc::mma_commit(smem_u32(&dkv_full));
+        if (last_of_bh) tc::mma_commit(smem_u32(&kv_empty[kb]));
+      }
+      __syncwarp();
+      if (last_of_bh || last_tile) ++flushes;
+      if (t + 2 < ntiles) issue_sdp(t + 2);
+    }
+  } else if (warp < 10) {
+    // ===== softmax / epilogue groups =====
+    const int g = (warp - 2) >> 2;
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    const uint32_t t_s = tmem + g * kTPair + kTS + lane_off, t_dp = tmem + g * kTPair + kTdP + lane_off;
+    const uint32_t row_off = (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u;
+    const int L = p.L;
+    const float sl2 = p.scale_log2, scale = p.scale;
+    int flushes = 0;   // counted identically in both groups and the MMA warp
+    int cur_bh = -1;
+    for (int t = 0; t < ntiles; ++t) {
+      const int item = item0 + t;
+      const int bh = item / tpb;
+      const bool last_tile = t + 1 == ntiles;
+      const bool flush = last_tile || ((item + 1) / tpb != bh);
+      if ((t & 1) != g) {            // the other group's tile: only keep the flush counter in step
+        if (flush) ++flushes;
+        continue;
+      }
+      const int b = bh / p.H, h = bh - b * p.H;
+      (void)cur_bh;
+      tc::mbar_wait(smem_u32(&sdp_full[g]), (uint32_t)(t >> 1) & 1u);
+      tc::fence_after_sync();
+
+      // ---- pass A: S -> e = exp2((s - max) * scale * log2 e), row sum --------------------------------------------
+      float e[kLP];
+      {
+        uint32_t sv[kLP];
+        uint32_t(&c0)[16] = *reinterpret_cast<uint32_t(*)[16]>(&sv[0]);
+        uint32_t(&c1)[16] = *reinterpret_cast<uint32_t(*)[16]>(&sv[16]);
+        uint32_t(&c2)[16] = *reinterpret_cast<uint32_t(*)[16]>(&sv[32]);
+        uint32_t(&c3)[16] = *reinterpret_cast<uint32_t(*)[16]>(&sv[48]);
+        uint32_t(&c4)[16] = *reinterpret_cast<uint32_t(*)[16]>(&sv[64]);
+        tc::tmem_ld16(t_s + 0, c0); tc::tmem_ld16(t_s + 16, c1); tc::tmem_ld16(t_s + 32, c2);
+        tc::tmem_ld16(t_s + 48, c3); tc::tmem_ld16(t_s + 64, c4);
+        tc::tmem_ld_wait();
+        float m = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < kLP; ++j) m = fmaxf(m, j < L ? __uint_as_float(sv[j]) : -INFINITY);
+        const float off = m * sl2;
+#pragma unroll
+        for (int j = 0; j < kLP; ++j) e[j] = j < L ? ex2(fmaf(__uint_as_float(sv[j]), sl2, -off)) : 0.f;
+      }
+      float sum = 0.f;
+#pragma unroll
+      for (int j = 0; j < kLP; ++j) sum += e[j];
+      const float inv = 1.0f / sum;
+
+      // ---- pass B: delta = sum_j P_j dP_j ---------------------------------------------------------------------------
+      float delta = 0.f;
+#pragma unroll
+      for (int c = 0; c < kLP / 16; ++c) {
+        uint32_t dv[16];
+        tc::tmem_ld16(t_dp + c * 16, dv);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) delta = fmaf(e[c * 16 + j], __uint_as_float(dv[j]), delta);
+      }
+      delta *= inv;
+
+      // ---- P / dS shared-memory tiles free?  (dK/dV MMAs of the previous tile have read them) ----------------------
+      if (t > 0) tc::mbar_wait(smem_u32(&pds_free), (uint32_t)(t - 1) & 1u);
+
+      // ---- pass C: dS = P o (dP - delta) * scale; P, dS -> smem (MN-major, swizzled); dS -> TMEM over dP -------------
+      const float ps = inv * scale;
+#pragma unroll
+      for (int c = 0; c < kLP / 16; ++c) {
+        uint32_t dv[16];
+        tc::tmem_ld16(t_dp + c * 16, dv);
+        tc::tmem_ld_wait();
+        uint32_t pp[8], dd[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float e0 = e[c * 16 + 2 * j], e1 = e[c * 16 + 2 * j + 1];
+          pp[j] = pack2<T>(e0 * inv, e1 * inv);
+          dd[j] = pack2<T>(e0 * ps * (__uint_as_float(dv[2 * j]) - delta), e1 * ps * (__uint_as_float(dv[2 * j + 1]) - delta));
+        }
+        tmem_st8(t_dp + c * 8, dd);   // columns [8c, 8c+8) <= [16c, 16c+16) already consumed above: in-place is safe
+#pragma unroll
+        for (int hlf = 0; hlf < 2; ++hlf) {
+          const int chunk = c * 2 + hlf;                       // 8 keys = 16 bytes
+          const uint32_t slab = (uint32_t)(chunk >> 3) * kSlab;
+          const uint32_t o = slab + row_off + (uint32_t)(((chunk & 7) ^ (row & 7)) << 4);
+          st_shared16(smem + kOffP + o, pp[hlf * 4 + 0], pp[hlf * 4 + 1], pp[hlf * 4 + 2], pp[hlf * 4 + 3]);
+          st_shared16(smem + kOffdS + o, dd[hlf * 4 + 0], dd[hlf * 4 + 1], dd[hlf * 4 + 2], dd[hlf * 4 + 3]);
+        }
+      }
+      tc::tmem_st_wait();
+      tc::fence_before_sync();
+      tc::fence_proxy_async_smem();     // P / dS written through the generic proxy -> visible to tcgen05.mma
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(smem_u32(&ds_ready[g]));
+
+      // ---- dQ epilogue: TMEM -> 16-bit -> swizzled staging tile -> (warp 10) TMA store -------------------------------
+      tc::mbar_wait(smem_u32(&dq_full), (uint32_t)t & 1u);
+      if (t > 0) tc::mbar_wait(smem_u32(&stage_free), (uint32_t)(t - 1) & 1u);   // previous store has read the staging tile
+      tc::fence_after_sync();
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t ov[32];
+        tc::tmem_ld32(tmem + kTdQ + lane_off + half * 32, ov);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int chunk = half * 4 + c;
+          const uint32_t addr = smem + kOffStage + (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4);
+          st_shared16(addr, pack2<T>(__uint_as_float(ov[c * 8 + 0]), __uint_as_float(ov[c * 8 + 1])),
+                      pack2<T>(__uint_as_float(ov[c * 8 + 2]), __uint_as_float(ov[c * 8 + 3])),
+                      pack2<T>(__uint_as_float(ov[c * 8 + 4]), __uint_as_float(ov[c * 8 + 5])),
+                      pack2<T>(__uint_as_float(ov[c * 8 + 6]), __uint_as_float(ov[c * 8 + 7])));
+        }
+      }
+      tc::fence_before_sync();
+      tc::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) { tc::mbar_arrive(smem_u32(&dq_free)); tc::mbar_arrive(smem_u32(&dq_staged)); }
+
+      // ---- (batch, head) boundary: drain dK / dV (lane = key) and add them to the global fp32 accumulators ----------
+      if (flush) {
+        tc::mbar_wait(smem_u32(&dkv_full), (uint32_t)flushes & 1u);
+        tc::fence_after_sync();
+        uint32_t kk[64], vv[64];
+        {
+          uint32_t(&k0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&kk[0]);
+          uint32_t(&k1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&kk[32]);
+          uint32_t(&v0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&vv[0]);
+          uint32_t(&v1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&vv[32]);
+          tc::tmem_ld32(tmem + kTdK + lane_off, k0); tc::tmem_ld32(tmem + kTdK + lane_off + 32, k1);
+          tc::tmem_ld32(tmem + kTdV + lane_off, v0); tc::tmem_ld32(tmem + kTdV + lane_off + 32, v1);
+          tc::tmem_ld_wait();
+        }
+        tc::fence_before_sync();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(smem_u32(&dkv_free));    // TMEM dK / dV may be overwritten by the next head
+        if (row < L) {
+          float* dkp = p.dk + (long long)b * p.bs_dkv + (long long)row * p.ld_dkv + h * kD;
+          float* dvp = p.dv + (long long)b * p.bs_dkv + (long long)row * p.ld_dkv + h * kD;
+          if (p.vec_atomics) {
+#pragma unroll
+            for (int d = 0; d < kD; d += 4) {
+              atomicAdd(reinterpret_cast<float4*>(dkp + d), make_float4(__uint_as_float(kk[d]), __uint_as_float(kk[d + 1]),
+                                                                         __uint_as_float(kk[d + 2]), __uint_as_float(kk[d + 3])));
+              atomicAdd(reinterpret_cast<float4*>(dvp + d), make_float4(__uint_as_float(vv[d]), __uint_as_float(vv[d + 1]),
+                                                                         __uint_as_float(vv[d + 2]), __uint_as_float(vv[d + 3])));
+            }
+          } else {
+#pragma unroll
+            for (int d = 0; d < kD; ++d) { atomicAdd(dkp + d, __uint_as_float(kk[d])); atomicAdd(dvp + d, __uint_as_float(vv[d])); }
+          }
+        }
+        ++flushes;
+      }
+    }
+  } else {
+    // ===== warp 10: dQ TMA-store issuer =====
+    for (int t = 0; t < ntiles; ++t) {
+      const int item = item0 + t;
+      const int bh = item / tpb, tile = item - bh * tpb;
+      const int b = bh / p.H, h = bh - b * p.H;
+      tc::mbar_wait(smem_u32(&dq_staged), (uint32_t)t & 1u);
+      if (tc::elect_one()) {
+        tc::tma_store_3d(&p.tmdQ, smem + kOffStage, h * kD, tile * kQT, b);
+        tc::tma_store_commit();
+        tc::tma_store_wait_read<0>();
+        tc::mbar_arrive(smem_u32(&stage_free));
+        if (t + 1 == ntiles) tc::tma_store_wait<0>();
+      }
+      __syncwarp();
+    }
+  }
+
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc::fence_after_sync();
+    tc::tmem_dealloc(tmem, kTmemCols);
+  }
+}
+
+template <typename T>
+int launch_bwd_tc(const BwdParams& p, int ctas, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    PEA_CUDA(cudaFuncSetAttribute(attn2_bwd_tc_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    attr_set = true;
+  }
+  attn2_bwd_tc_kernel<T><<<ctas, kThreads, kSmemBytes, st>>>(p);
+  PEA_LAUNCH_CHECK();
+  return PEA_OK;
+}
+
+}  // namespace
+
+bool attn2_bwd_tc_eligible(const pea_attn2_desc* a) {
+  if (a->d != kD || a->L > kLP) return false;
+  const long long voff = (static_cast<const char*>(a->d_v) - static_cast<const char*>(a->d_k)) / 2;
+  const int C = a->H * a->d;
+  auto al16 = [](const void* x) { return (reinterpret_cast<uintptr_t>(x) & 15) == 0; };
+  return voff >= C && voff + C <= a->ld_kv && voff % 8 == 0 && a->ld_q % 8 == 0 && a->ld_do % 8 == 0 && a->ld_dq % 8 == 0 &&
+         a->ld_kv % 8 == 0 && a->bs_kv % 8 == 0 && al16(a->d_q) && al16(a->d_k) && al16(a->d_do) && al16(a->d_dq);
+}
+
+int attn2_bwd_tc(const pea_attn2_desc* a, cudaStream_t st) {
+  BwdParams p{};
+  const bool fp16 = a->dtype == PEA_F16;
+  const int C = a->H * a->d;
+  p.B = a->B; p.N = a->N; p.L = a->L; p.H = a->H;
+  p.scale = a->scale;
+  p.scale_log2 = a->scale * 1.4426950408889634f;
+  const uint64_t dims[3] = {(uint64_t)C, (uint64_t)a->N, (uint64_t)a->B};
+  const uint32_t box[3] = {64, 128, 1};
+  struct { CUtensorMap* m; const void* ptr; long long ld; } maps[3] = {{&p.tmQ, a->d_q, a->ld_q}, {&p.tmdO, a->d_do, a->ld_do}, {&p.tmdQ, a->d_dq, a->ld_dq}};
+  for (auto& m : maps) {
+    const uint64_t str[2] = {(uint64_t)m.ld * 2, (uint64_t)m.ld * 2 * (uint64_t)a->N};
+    int rc = encode_tmap_16bit(m.m, m.ptr, 3, dims, str, box, fp16);
+    if (rc != PEA_OK) return rc;
+  }
+  {
+    const long long voff = (static_cast<const char*>(a->d_v) - static_cast<const char*>(a->d_k)) / 2;
+    const uint64_t kdims[3] = {(uint64_t)(voff + C), (uint64_t)a->L, (uint64_t)a->B};
+    const uint64_t str[2] = {(uint64_t)a->ld_kv * 2, (uint64_t)a->bs_kv * 2};
+    const uint32_t kbox[3] = {64, (uint32_t)kLP, 1};
+    int rc = encode_tmap_16bit(&p.tmKV, a->d_k, 3, kdims, str, kbox, fp16);
+    if (rc != PEA_OK) return rc;
+    p.voff = (int)voff;
+  }
+  p.tiles_per_bh = (a->N + kQT - 1) / kQT;
+  p.total_tiles = a->B * a->H * p.tiles_per_bh;
+  const int slots = num_sms();
+  p.tiles_per_cta = (p.total_tiles + slots - 1) / slots;
+  const int ctas = (p.total_tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
+  const int fmt = fp16 ? 0 : 1;
+  p.idesc_s = tc::make_idesc(fmt, 128, kLP, 0, 0);
+  p.idesc_dq = tc::make_idesc(fmt, 128, kD, 0, 1);
+  p.idesc_dkv = tc::make_idesc(fmt, 128, kD, 1, 1);
+  p.dk = a->d_dk; p.dv = a->d_dv; p.ld_dkv = a->ld_dkv; p.bs_dkv = a->bs_dkv;
+  p.vec_atomics = (a->ld_dkv % 4 == 0) && (a->bs_dkv % 4 == 0) && ((reinterpret_cast<uintptr_t>(a->d_dk) & 15) == 0) &&
+                  ((reinterpret_cast<uintptr_t>(a->d_dv) & 15) == 0);
+  return fp16 ? launch_bwd_tc<__half>(p, ctas, st) : launch_bwd_tc<__nv_bfloat16>(p, ctas, st);
+}
+
+}  // namespace pea

@@ -410,6 +410,8 @@ int validate(const pea_attn2_desc* a, bool bwd, AttnParams& p) {
 namespace pea {
 int attn2_fwd_tc(const pea_attn2_desc* a, cudaStream_t st);   // attn2_tc.cu
 bool attn2_fwd_tc_eligible(const pea_attn2_desc* a);
+int attn2_bwd_tc(const pea_attn2_desc* a, cudaStream_t st);   // attn2_bwd_tc.cu
+bool attn2_bwd_tc_eligible(const pea_attn2_desc* a);
 }  // namespace pea
 
 using namespace pea;
@@ -460,5 +462,6 @@ extern "C" int pea_attn2_bwd(const pea_attn2_desc* desc, void* stream) {
   int rc = validate(desc, true, p);
   if (rc != PEA_OK) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (use_tc_path() && attn2_bwd_tc_eligible(desc)) return attn2_bwd_tc(desc, st);
   PEA_DISPATCH_ATTN(launch_bwd);
 }
