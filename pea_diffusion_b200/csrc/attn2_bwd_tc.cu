@@ -61,7 +61,6 @@ __device__ __forceinline__ float ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 __device__ __forceinline__ void st_shared16(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
@@ -234,7 +233,9 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_bwd_tc_kernel(const __grid_
       tc::mbar_wait(smem_u32(&sdp_full[g]), (uint32_t)(t >> 1) & 1u);
       tc::fence_after_sync();
 
-      // ---- pass A: S -> e = exp2((s - max) * scale * log2 e), row sum --------------------------------------------
+      // Columns >= L hold S = 0 (K rows beyond L are zero-filled), never NaN: only the chunk that straddles L needs
+      // masking, and "(c + 1) * 16 <= L" is warp-uniform.
+      // ---- pass A: S -> e = exp2((s - max) * scale * log2 e), row sum ---------------------------------------------
       float e[kLP];
       {
         uint32_t sv[kLP];
@@ -248,10 +249,26 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_bwd_tc_kernel(const __grid_
         tc::tmem_ld_wait();
         float m = -INFINITY;
 #pragma unroll
-        for (int j = 0; j < kLP; ++j) m = fmaxf(m, j < L ? __uint_as_float(sv[j]) : -INFINITY);
+        for (int c = 0; c < kLP / 16; ++c) {
+          if ((c + 1) * 16 <= L) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) m = fmaxf(m, __uint_as_float(sv[c * 16 + j]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) m = fmaxf(m, c * 16 + j < L ? __uint_as_float(sv[c * 16 + j]) : -INFINITY);
+          }
+        }
         const float off = m * sl2;
 #pragma unroll
-        for (int j = 0; j < kLP; ++j) e[j] = j < L ? ex2(fmaf(__uint_as_float(sv[j]), sl2, -off)) : 0.f;
+        for (int c = 0; c < kLP / 16; ++c) {
+          if ((c + 1) * 16 <= L) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) e[c * 16 + j] = ex2(fmaf(__uint_as_float(sv[c * 16 + j]), sl2, -off));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) e[c * 16 + j] = c * 16 + j < L ? ex2(fmaf(__uint_as_float(sv[c * 16 + j]), sl2, -off)) : 0.f;
+          }
+        }
       }
       float sum = 0.f;
 #pragma unroll
@@ -270,32 +287,32 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_bwd_tc_kernel(const __grid_
       }
       delta *= inv;
 
-      // ---- P / dS shared-memory tiles free?  (dK/dV MMAs of the previous tile have read them) ----------------------
-      if (t > 0) tc::mbar_wait(smem_u32(&pds_free), (uint32_t)(t - 1) & 1u);
-
-      // ---- pass C: dS = P o (dP - delta) * scale; P, dS -> smem (MN-major, swizzled); dS -> TMEM over dP -------------
+      // ---- pass C: dS = P o (dP - delta) * scale, P: 16-bit pairs in registers; dS -> TMEM over dP -------------------
       const float ps = inv * scale;
+      uint32_t pp[kLP / 2], dd[kLP / 2];
 #pragma unroll
       for (int c = 0; c < kLP / 16; ++c) {
         uint32_t dv[16];
         tc::tmem_ld16(t_dp + c * 16, dv);
         tc::tmem_ld_wait();
-        uint32_t pp[8], dd[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float e0 = e[c * 16 + 2 * j], e1 = e[c * 16 + 2 * j + 1];
-          pp[j] = pack2<T>(e0 * inv, e1 * inv);
-          dd[j] = pack2<T>(e0 * ps * (__uint_as_float(dv[2 * j]) - delta), e1 * ps * (__uint_as_float(dv[2 * j + 1]) - delta));
+          pp[c * 8 + j] = pack2<T>(e0 * inv, e1 * inv);
+          dd[c * 8 + j] = pack2<T>(e0 * ps * (__uint_as_float(dv[2 * j]) - delta), e1 * ps * (__uint_as_float(dv[2 * j + 1]) - delta));
         }
-        tmem_st8(t_dp + c * 8, dd);   // columns [8c, 8c+8) <= [16c, 16c+16) already consumed above: in-place is safe
+        uint32_t(&d8)[8] = *reinterpret_cast<uint32_t(*)[8]>(&dd[c * 8]);
+        tmem_st8(t_dp + c * 8, d8);   // columns [8c, 8c+8) <= [16c, 16c+16) already consumed above: in-place is safe
+      }
+
+      // ---- P / dS shared-memory tiles free?  (dK/dV MMAs of the previous tile have read them) -- only the stores wait
+      if (t > 0) tc::mbar_wait(smem_u32(&pds_free), (uint32_t)(t - 1) & 1u);
 #pragma unroll
-        for (int hlf = 0; hlf < 2; ++hlf) {
-          const int chunk = c * 2 + hlf;                       // 8 keys = 16 bytes
-          const uint32_t slab = (uint32_t)(chunk >> 3) * kSlab;
-          const uint32_t o = slab + row_off + (uint32_t)(((chunk & 7) ^ (row & 7)) << 4);
-          st_shared16(smem + kOffP + o, pp[hlf * 4 + 0], pp[hlf * 4 + 1], pp[hlf * 4 + 2], pp[hlf * 4 + 3]);
-          st_shared16(smem + kOffdS + o, dd[hlf * 4 + 0], dd[hlf * 4 + 1], dd[hlf * 4 + 2], dd[hlf * 4 + 3]);
-        }
+      for (int chunk = 0; chunk < kLP / 8; ++chunk) {          // 8 keys = 16 bytes; MN-major, 128B swizzle
+        const uint32_t slab = (uint32_t)(chunk >> 3) * kSlab;
+        const uint32_t o = slab + row_off + (uint32_t)(((chunk & 7) ^ (row & 7)) << 4);
+        st_shared16(smem + kOffP + o, pp[chunk * 4 + 0], pp[chunk * 4 + 1], pp[chunk * 4 + 2], pp[chunk * 4 + 3]);
+        st_shared16(smem + kOffdS + o, dd[chunk * 4 + 0], dd[chunk * 4 + 1], dd[chunk * 4 + 2], dd[chunk * 4 + 3]);
       }
       tc::tmem_st_wait();
       tc::fence_before_sync();
@@ -347,17 +364,12 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_bwd_tc_kernel(const __grid_
         if (row < L) {
           float* dkp = p.dk + (long long)b * p.bs_dkv + (long long)row * p.ld_dkv + h * kD;
           float* dvp = p.dv + (long long)b * p.bs_dkv + (long long)row * p.ld_dkv + h * kD;
-          if (p.vec_atomics) {
 #pragma unroll
-            for (int d = 0; d < kD; d += 4) {
-              atomicAdd(reinterpret_cast<float4*>(dkp + d), make_float4(__uint_as_float(kk[d]), __uint_as_float(kk[d + 1]),
-                                                                         __uint_as_float(kk[d + 2]), __uint_as_float(kk[d + 3])));
-              atomicAdd(reinterpret_cast<float4*>(dvp + d), make_float4(__uint_as_float(vv[d]), __uint_as_float(vv[d + 1]),
-                                                                         __uint_as_float(vv[d + 2]), __uint_as_float(vv[d + 3])));
-            }
-          } else {
-#pragma unroll
-            for (int d = 0; d < kD; ++d) { atomicAdd(dkp + d, __uint_as_float(kk[d])); atomicAdd(dvp + d, __uint_as_float(vv[d])); }
+          for (int d = 0; d < kD; d += 4) {
+            atomicAdd(reinterpret_cast<float4*>(dkp + d), make_float4(__uint_as_float(kk[d]), __uint_as_float(kk[d + 1]),
+                                                                       __uint_as_float(kk[d + 2]), __uint_as_float(kk[d + 3])));
+            atomicAdd(reinterpret_cast<float4*>(dvp + d), make_float4(__uint_as_float(vv[d]), __uint_as_float(vv[d + 1]),
+                                                                       __uint_as_float(vv[d + 2]), __uint_as_float(vv[d + 3])));
           }
         }
         ++flushes;
@@ -409,7 +421,8 @@ bool attn2_bwd_tc_eligible(const pea_attn2_desc* a) {
   const int C = a->H * a->d;
   auto al16 = [](const void* x) { return (reinterpret_cast<uintptr_t>(x) & 15) == 0; };
   return voff >= C && voff + C <= a->ld_kv && voff % 8 == 0 && a->ld_q % 8 == 0 && a->ld_do % 8 == 0 && a->ld_dq % 8 == 0 &&
-         a->ld_kv % 8 == 0 && a->bs_kv % 8 == 0 && al16(a->d_q) && al16(a->d_k) && al16(a->d_do) && al16(a->d_dq);
+         a->ld_kv % 8 == 0 && a->bs_kv % 8 == 0 && al16(a->d_q) && al16(a->d_k) && al16(a->d_do) && al16(a->d_dq) &&
+         a->ld_dkv % 4 == 0 && a->bs_dkv % 4 == 0 && al16(a->d_dk) && al16(a->d_dv);   // float4 atomics on dK / dV
 }
 
 int attn2_bwd_tc(const pea_attn2_desc* a, cudaStream_t st) {
@@ -446,8 +459,7 @@ int attn2_bwd_tc(const pea_attn2_desc* a, cudaStream_t st) {
   p.idesc_dq = tc::make_idesc(fmt, 128, kD, 0, 1);
   p.idesc_dkv = tc::make_idesc(fmt, 128, kD, 1, 1);
   p.dk = a->d_dk; p.dv = a->d_dv; p.ld_dkv = a->ld_dkv; p.bs_dkv = a->bs_dkv;
-  p.vec_atomics = (a->ld_dkv % 4 == 0) && (a->bs_dkv % 4 == 0) && ((reinterpret_cast<uintptr_t>(a->d_dk) & 15) == 0) &&
-                  ((reinterpret_cast<uintptr_t>(a->d_dv) & 15) == 0);
+  p.vec_atomics = 1;
   return fp16 ? launch_bwd_tc<__half>(p, ctas, st) : launch_bwd_tc<__nv_bfloat16>(p, ctas, st);
 }
 
