@@ -275,15 +275,20 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_bwd_tc_kernel(const __grid_
       for (int j = 0; j < kLP; ++j) sum += e[j];
       const float inv = 1.0f / sum;
 
-      // ---- pass B: delta = sum_j P_j dP_j ---------------------------------------------------------------------------
+      // ---- pass B: delta = sum_j P_j dP_j.  TMEM loads are software-pipelined: chunk c+1 is in flight while chunk c
+      //      is consumed (tcgen05.wait::ld right after every load would expose its full latency ten times per tile).
       float delta = 0.f;
+      uint32_t dva[16], dvb[16];
+      tc::tmem_ld16(t_dp, dva);
+      tc::tmem_ld_wait();
 #pragma unroll
       for (int c = 0; c < kLP / 16; ++c) {
-        uint32_t dv[16];
-        tc::tmem_ld16(t_dp + c * 16, dv);
-        tc::tmem_ld_wait();
+        uint32_t(&cur)[16] = (c & 1) ? dvb : dva;
+        uint32_t(&nxt)[16] = (c & 1) ? dva : dvb;
+        tc::tmem_ld16(t_dp + ((c + 1 < kLP / 16) ? (c + 1) * 16 : 0), nxt);   // last iteration prefetches pass C's chunk 0
 #pragma unroll
-        for (int j = 0; j < 16; ++j) delta = fmaf(e[c * 16 + j], __uint_as_float(dv[j]), delta);
+        for (int j = 0; j < 16; ++j) delta = fmaf(e[c * 16 + j], __uint_as_float(cur[j]), delta);
+        tc::tmem_ld_wait();
       }
       delta *= inv;
 
@@ -292,17 +297,19 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_bwd_tc_kernel(const __grid_
       uint32_t pp[kLP / 2], dd[kLP / 2];
 #pragma unroll
       for (int c = 0; c < kLP / 16; ++c) {
-        uint32_t dv[16];
-        tc::tmem_ld16(t_dp + c * 16, dv);
-        tc::tmem_ld_wait();
+        // kLP / 16 = 5 is odd, so pass B's last prefetch (chunk 0) landed in dvb: chunk c lives in (c even ? dvb : dva)
+        uint32_t(&cur)[16] = (c & 1) ? dva : dvb;
+        uint32_t(&nxt)[16] = (c & 1) ? dvb : dva;
+        if (c + 1 < kLP / 16) tc::tmem_ld16(t_dp + (c + 1) * 16, nxt);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float e0 = e[c * 16 + 2 * j], e1 = e[c * 16 + 2 * j + 1];
           pp[c * 8 + j] = pack2<T>(e0 * inv, e1 * inv);
-          dd[c * 8 + j] = pack2<T>(e0 * ps * (__uint_as_float(dv[2 * j]) - delta), e1 * ps * (__uint_as_float(dv[2 * j + 1]) - delta));
+          dd[c * 8 + j] = pack2<T>(e0 * ps * (__uint_as_float(cur[2 * j]) - delta), e1 * ps * (__uint_as_float(cur[2 * j + 1]) - delta));
         }
+        if (c + 1 < kLP / 16) tc::tmem_ld_wait();   // chunk c+1 (columns >= 16(c+1)) is in registers before columns [8c, 8c+8) are overwritten
         uint32_t(&d8)[8] = *reinterpret_cast<uint32_t(*)[8]>(&dd[c * 8]);
-        tmem_st8(t_dp + c * 8, d8);   // columns [8c, 8c+8) <= [16c, 16c+16) already consumed above: in-place is safe
+        tmem_st8(t_dp + c * 8, d8);
       }
 
       // ---- P / dS shared-memory tiles free?  (dK/dV MMAs of the previous tile have read them) -- only the stores wait
@@ -324,19 +331,20 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_bwd_tc_kernel(const __grid_
       tc::mbar_wait(smem_u32(&dq_full), (uint32_t)t & 1u);
       if (t > 0) tc::mbar_wait(smem_u32(&stage_free), (uint32_t)(t - 1) & 1u);   // previous store has read the staging tile
       tc::fence_after_sync();
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        uint32_t ov[32];
-        tc::tmem_ld32(tmem + kTdQ + lane_off + half * 32, ov);
+      {
+        uint32_t ov[64];
+        uint32_t(&o0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&ov[0]);
+        uint32_t(&o1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&ov[32]);
+        tc::tmem_ld32(tmem + kTdQ + lane_off, o0);
+        tc::tmem_ld32(tmem + kTdQ + lane_off + 32, o1);
         tc::tmem_ld_wait();
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const int chunk = half * 4 + c;
+        for (int chunk = 0; chunk < 8; ++chunk) {
           const uint32_t addr = smem + kOffStage + (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4);
-          st_shared16(addr, pack2<T>(__uint_as_float(ov[c * 8 + 0]), __uint_as_float(ov[c * 8 + 1])),
-                      pack2<T>(__uint_as_float(ov[c * 8 + 2]), __uint_as_float(ov[c * 8 + 3])),
-                      pack2<T>(__uint_as_float(ov[c * 8 + 4]), __uint_as_float(ov[c * 8 + 5])),
-                      pack2<T>(__uint_as_float(ov[c * 8 + 6]), __uint_as_float(ov[c * 8 + 7])));
+          st_shared16(addr, pack2<T>(__uint_as_float(ov[chunk * 8 + 0]), __uint_as_float(ov[chunk * 8 + 1])),
+                      pack2<T>(__uint_as_float(ov[chunk * 8 + 2]), __uint_as_float(ov[chunk * 8 + 3])),
+                      pack2<T>(__uint_as_float(ov[chunk * 8 + 4]), __uint_as_float(ov[chunk * 8 + 5])),
+                      pack2<T>(__uint_as_float(ov[chunk * 8 + 6]), __uint_as_float(ov[chunk * 8 + 7])));
         }
       }
       tc::fence_before_sync();

@@ -248,19 +248,20 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_fwd_tc_kernel(const __grid_
       }
       tc::mbar_wait(smem_u32(&o_full[g]), ph);
       tc::fence_after_sync();
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        uint32_t ov[32];
-        tc::tmem_ld32(t_o + half * 32, ov);
+      {
+        uint32_t ov[64];
+        uint32_t(&o0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&ov[0]);
+        uint32_t(&o1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&ov[32]);
+        tc::tmem_ld32(t_o, o0);
+        tc::tmem_ld32(t_o + 32, o1);
         tc::tmem_ld_wait();
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int chunk = 0; chunk < 8; ++chunk) {   // 16-byte chunk of the 128-byte row; TMA SWIZZLE_128B: chunk ^= row % 8
           uint4 u;
-          u.x = pack2<T>(__uint_as_float(ov[c * 8 + 0]) * inv, __uint_as_float(ov[c * 8 + 1]) * inv);
-          u.y = pack2<T>(__uint_as_float(ov[c * 8 + 2]) * inv, __uint_as_float(ov[c * 8 + 3]) * inv);
-          u.z = pack2<T>(__uint_as_float(ov[c * 8 + 4]) * inv, __uint_as_float(ov[c * 8 + 5]) * inv);
-          u.w = pack2<T>(__uint_as_float(ov[c * 8 + 6]) * inv, __uint_as_float(ov[c * 8 + 7]) * inv);
-          const int chunk = half * 4 + c;  // 16-byte chunk of the 128-byte row; TMA SWIZZLE_128B: chunk ^= row % 8
+          u.x = pack2<T>(__uint_as_float(ov[chunk * 8 + 0]) * inv, __uint_as_float(ov[chunk * 8 + 1]) * inv);
+          u.y = pack2<T>(__uint_as_float(ov[chunk * 8 + 2]) * inv, __uint_as_float(ov[chunk * 8 + 3]) * inv);
+          u.z = pack2<T>(__uint_as_float(ov[chunk * 8 + 4]) * inv, __uint_as_float(ov[chunk * 8 + 5]) * inv);
+          u.w = pack2<T>(__uint_as_float(ov[chunk * 8 + 6]) * inv, __uint_as_float(ov[chunk * 8 + 7]) * inv);
           const uint32_t addr = o_stage + (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4);
           asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w) : "memory");
         }
