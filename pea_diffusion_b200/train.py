@@ -113,7 +113,7 @@ class GradAllReducer:
     side stream; ``finish()`` joins before the optimizer step.  Backend-agnostic: NCCL on GPUs, gloo in the CPU tests.
     """
 
-    def __init__(self, params, process_group=None):
+    def __init__(self, params, process_group=None, hooks: bool = True):
         self.params = [p for p in params if p.requires_grad]
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
@@ -122,9 +122,17 @@ class GradAllReducer:
         on_gpu = len(self.params) > 0 and all(p.is_cuda for p in self.params)
         self._comm_stream = torch.cuda.Stream() if (self.world > 1 and on_gpu) else None
         self.bytes_per_step = sum(p.numel() * p.element_size() for p in self.params)
-        if self.world > 1:
+        if self.world > 1 and hooks:
             for p in self.params:
                 self._hooks.append(p.register_post_accumulate_grad_hook(self._grad_ready))
+
+    def reduce_now(self) -> None:
+        """Explicit variant for CUDA-graph replays (autograd hooks do not fire on replay): launch every tensor's
+        all-reduce, last-produced gradient first."""
+        if self.world > 1:
+            for p in reversed(self.params):
+                if p.grad is not None:
+                    self._grad_ready(p)
 
     def _grad_ready(self, p: Tensor) -> None:
         if self._comm_stream is not None:
@@ -155,11 +163,16 @@ class KDTrainer:
     One process per GPU; every rank holds full replicas of both UNets and the adapter; the only exchange per step is
     the mean all-reduce of the adapter gradients (6.03 M parameters, ``GradAllReducer``), then an identical AdamW step
     on every rank (replaces the reference's ZeRO-1 sharding, train_sdxl_zh.sh:22-31).
+
+    ``cuda_graph=True`` captures forward + backward of the step (adapter, both UNets, loss: every kernel of this
+    library and of the PyTorch shell) into ONE CUDA graph on the first call and replays it afterwards; batches are
+    copied into the graph's static input buffers.  The all-reduce and the fused AdamW step stay outside the graph.
+    This removes the Python / launch overhead of the ~10^4 launches per step; shapes must then stay fixed.
     """
 
     def __init__(self, student: nn.Module, teacher: nn.Module, adapter: nn.Module, variant: str = "sdxl", lr: float = 1e-5,
                  betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0, feature_weight: float = 0.1,
-                 process_group=None):
+                 process_group=None, cuda_graph: bool = False):
         self.student, self.teacher, self.adapter, self.variant = student, teacher, adapter, variant
         self.feature_weight = feature_weight
         self.taps_s, self.taps_t = KDTaps(student), KDTaps(teacher)
@@ -168,19 +181,51 @@ class KDTrainer:
         # utils/model_utils.py:52-71: AdamW on the adapter only; the --weight_decay flag never reaches the param
         # group, so the effective decay is 0
         self.opt = torch.optim.AdamW(params, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, fused=fused)
-        self.reducer = GradAllReducer(params, process_group)
+        self.cuda_graph = cuda_graph
+        self.reducer = GradAllReducer(params, process_group, hooks=not cuda_graph)
+        self._graph = None
+        self._static_in: Dict[str, Tensor] = {}
+        self._static_out: Optional[Tensor] = None
 
-    def step(self, batch: Mapping[str, Tensor]) -> Tensor:
-        """forward + backward + (all-reduce) + AdamW.  Returns the device tensor [L, L0, L1, L2]; no host sync."""
-        self.opt.zero_grad(set_to_none=True)
+    def _forward_backward(self, batch: Mapping[str, Tensor]) -> Tensor:
         loss, l0, l1, l2 = kd_forward(self.student, self.teacher, self.adapter, batch, self.taps_s, self.taps_t, self.variant,
                                       self.feature_weight)
         loss.backward()
-        self.reducer.finish()
-        self.opt.step()
         self.taps_s.clear()
         self.taps_t.clear()
         return torch.stack([loss.detach(), l0, l1, l2])
+
+    def _capture(self, batch: Mapping[str, Tensor]) -> None:
+        self._static_in = {k: v.clone() for k, v in batch.items()}
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):   # warm-up off the capture stream: lazy initialisation, allocator, autotuners
+            for _ in range(2):
+                self.opt.zero_grad(set_to_none=True)
+                self._forward_backward(self._static_in)
+        torch.cuda.current_stream().wait_stream(side)
+        self.opt.zero_grad(set_to_none=True)
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._static_out = self._forward_backward(self._static_in)
+
+    def step(self, batch: Mapping[str, Tensor]) -> Tensor:
+        """forward + backward + (all-reduce) + AdamW.  Returns the device tensor [L, L0, L1, L2]; no host sync."""
+        if self.cuda_graph:
+            if self._graph is None:
+                self._capture(batch)
+            for k, v in batch.items():
+                self._static_in[k].copy_(v, non_blocking=True)
+            self._graph.replay()     # gradients land in the static .grad tensors the capture created
+            self.reducer.reduce_now()
+            self.reducer.finish()
+            self.opt.step()
+            return self._static_out
+        self.opt.zero_grad(set_to_none=True)
+        out = self._forward_backward(batch)
+        self.reducer.finish()
+        self.opt.step()
+        return out
 
     def close(self) -> None:
         self.reducer.close()
