@@ -7,10 +7,12 @@
 //             fp32-accurate mode all live in the epilogue;
 //           * attn2's to_k / to_v projections of the context (diffusers AttnProcessor2_0) and dContext = dK Wk + dV Wv.
 //
-// Structure (one 128 x 128 output tile per CTA, 192 threads):
-//   warp 0      TMA producer: 128B-swizzled [128 x 64] operand tiles, `stages`-deep mbarrier ring
-//   warp 1      TMEM allocator + MMA issuer: one thread issues tcgen05.mma (M128 N128 K16, kind::f16, fp32 accumulate
-//               in TMEM); tcgen05.commit releases smem stages and finally signals the epilogue
+// Structure (persistent CTAs, 128 x BN output tiles with BN = 128 or 256, 192 threads):
+//   warp 0      TMA producer: 128B-swizzled [128 x 64] / [BN x 64] operand tiles, `stages`-deep mbarrier ring that runs
+//               across tile boundaries
+//   warp 1      TMEM allocator + MMA issuer: one elected lane issues tcgen05.mma (M128 N{128,256} K16, kind::f16, fp32
+//               accumulate); accumulators are DOUBLE BUFFERED in TMEM (2 x BN columns) so tile i+1's main loop runs
+//               while the epilogue drains tile i; tcgen05.commit releases smem stages and signals the epilogue
 //   warps 2..5  epilogue: tcgen05.ld (each warp its 32-lane TMEM quadrant, thread = output row), fused math, stores
 // Operand majors: K-major tiles come from one {64, 128} TMA box; MN-major tiles (A^T / B^T stored row-major) from two
 // {64, 64} boxes, consumed through MN-major UMMA descriptors -- so dX = dY W and dW = dY^T X need no transposes.
@@ -23,12 +25,11 @@
 namespace pea {
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 64;
-constexpr int kTileBytes = BM * BK * 2;  // 16 KiB per operand plane per stage
-constexpr int kMaxStages = 6;
+constexpr int BM = 128, BK = 64;
+constexpr int kTileBytes = BM * BK * 2;  // 16 KiB per 128-row operand plane per stage
+constexpr int kMaxStages = 8;
 constexpr int kThreads = 192;
-constexpr uint32_t kTmemCols = 128;
-constexpr size_t kSmemBudget = 200 * 1024;
+constexpr size_t kSmemBudget = 208 * 1024;
 
 struct GemmParams {
   CUtensorMap tmA[3];
@@ -37,6 +38,7 @@ struct GemmParams {
   int sa, sb;
   int a_mn, b_mn;
   int kb_total, kb_per_split;
+  int m_tiles, n_tiles, splits, total_tiles;
   int stages;
   uint32_t idesc;
   float alpha;
@@ -151,23 +153,30 @@ __device__ __forceinline__ float round16(float v, int dtype) {
 // and descriptor arithmetic on the uniform datapath) and only the asynchronous instruction itself is issued by one
 // elected lane.  A single-lane loop with runtime plane / major branches measured ~430 cycles between MMAs (the
 // 128x128x16 MMA itself takes 64): r1 ncu capture profiles/gemm_r1_before.txt.
-template <int SA, int SB, int A_MN, int B_MN>
+template <int SA, int SB, int A_MN, int B_MN, int BN>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
-  __shared__ __align__(8) uint64_t acc_bar;
+  __shared__ __align__(8) uint64_t acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_slot;
 
   constexpr int S = SA > SB ? SA : SB;
-  constexpr uint32_t kStageBytes = (uint32_t)(SA + SB) * kTileBytes;
+  constexpr uint32_t kBTile = (uint32_t)BN * BK * 2;                       // B plane bytes per stage
+  constexpr uint32_t kStageBytes = (uint32_t)SA * kTileBytes + (uint32_t)SB * kBTile;
+  constexpr uint32_t kTmemCols = 2 * BN;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-  const int kb_begin = blockIdx.z * p.kb_per_split;
-  const int kb_end = min(p.kb_total, kb_begin + p.kb_per_split);
-  const int nkb = kb_end - kb_begin;  // >= 1 by construction
   const uint32_t tiles = (smem_u32(smem_raw) + 1023u) & ~1023u;  // 128B swizzle atoms need 1024-byte alignment
   const int stages = p.stages;
+  // tile index -> (split, n tile, m tile), m fastest: CTAs that run together share B (weight) tiles through L2
+  auto tile_coords = [&](int tile, int& m0, int& n0, int& kb_begin, int& nkb) {
+    const int mi = tile % p.m_tiles;
+    const int rest = tile / p.m_tiles;
+    const int ni = rest % p.n_tiles, z = rest / p.n_tiles;
+    m0 = mi * BM; n0 = ni * BN;
+    kb_begin = z * p.kb_per_split;
+    nkb = min(p.kb_total, kb_begin + p.kb_per_split) - kb_begin;
+  };
 
   if (warp == 0 && lane == 0) {
 #pragma unroll
@@ -178,7 +187,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       tc::mbar_init(smem_u32(&full_bar[s]), 1);
       tc::mbar_init(smem_u32(&empty_bar[s]), 1);
     }
-    tc::mbar_init(smem_u32(&acc_bar), 1);
+    tc::mbar_init(smem_u32(&acc_full[0]), 1); tc::mbar_init(smem_u32(&acc_full[1]), 1);
+    tc::mbar_init(smem_u32(&acc_empty[0]), 4); tc::mbar_init(smem_u32(&acc_empty[1]), 4);
     tc::fence_mbar_init();
   }
   if (warp == 1) tc::tmem_alloc(smem_u32(&tmem_base_slot), kTmemCols);
@@ -191,28 +201,35 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     // ===== TMA producer (whole warp loops; one elected lane issues) =====
     int s = 0;
     uint32_t ph = 0;
-    for (int it = 0; it < nkb; ++it) {
-      tc::mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
-      if (tc::elect_one()) {
-        const uint32_t fb = smem_u32(&full_bar[s]);
-        tc::mbar_expect_tx(fb, kStageBytes);
-        const int k0 = (kb_begin + it) * BK;
-        const uint32_t dst = tiles + (uint32_t)s * kStageBytes;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      int m0, n0, kb_begin, nkb;
+      tile_coords(tile, m0, n0, kb_begin, nkb);
+      for (int it = 0; it < nkb; ++it) {
+        tc::mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
+        if (tc::elect_one()) {
+          const uint32_t fb = smem_u32(&full_bar[s]);
+          tc::mbar_expect_tx(fb, kStageBytes);
+          const int k0 = (kb_begin + it) * BK;
+          const uint32_t dst = tiles + (uint32_t)s * kStageBytes;
 #pragma unroll
-        for (int i = 0; i < SA; ++i) {
-          const uint32_t d = dst + (uint32_t)i * kTileBytes;
-          if (!A_MN) tc::tma_load_2d(d, &p.tmA[i], fb, k0, m0);
-          else { tc::tma_load_2d(d, &p.tmA[i], fb, m0, k0); tc::tma_load_2d(d + kTileBytes / 2, &p.tmA[i], fb, m0 + 64, k0); }
-        }
+          for (int i = 0; i < SA; ++i) {
+            const uint32_t d = dst + (uint32_t)i * kTileBytes;
+            if (!A_MN) tc::tma_load_2d(d, &p.tmA[i], fb, k0, m0);
+            else { tc::tma_load_2d(d, &p.tmA[i], fb, m0, k0); tc::tma_load_2d(d + 8192, &p.tmA[i], fb, m0 + 64, k0); }
+          }
 #pragma unroll
-        for (int j = 0; j < SB; ++j) {
-          const uint32_t d = dst + (uint32_t)(SA + j) * kTileBytes;
-          if (!B_MN) tc::tma_load_2d(d, &p.tmB[j], fb, k0, n0);
-          else { tc::tma_load_2d(d, &p.tmB[j], fb, n0, k0); tc::tma_load_2d(d + kTileBytes / 2, &p.tmB[j], fb, n0 + 64, k0); }
+          for (int j = 0; j < SB; ++j) {
+            const uint32_t d = dst + (uint32_t)SA * kTileBytes + (uint32_t)j * kBTile;
+            if (!B_MN) tc::tma_load_2d(d, &p.tmB[j], fb, k0, n0);
+            else {
+#pragma unroll
+              for (int c = 0; c < BN / 64; ++c) tc::tma_load_2d(d + c * 8192, &p.tmB[j], fb, n0 + c * 64, k0);
+            }
+          }
         }
+        __syncwarp();
+        if (++s == stages) { s = 0; ph ^= 1u; }
       }
-      __syncwarp();
-      if (++s == stages) { s = 0; ph ^= 1u; }
     }
   } else if (warp == 1) {
     // ===== MMA issuer (whole warp loops; one elected lane issues tcgen05.mma / tcgen05.commit) =====
@@ -225,49 +242,63 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     const uint32_t idesc = p.idesc;
     int s = 0;
     uint32_t ph = 0;
-    for (int it = 0; it < nkb; ++it) {
-      tc::mbar_wait(smem_u32(&full_bar[s]), ph);
+    int local = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++local) {
+      int m0, n0, kb_begin, nkb;
+      tile_coords(tile, m0, n0, kb_begin, nkb);
+      const int as = local & 1;
+      const uint32_t tmem_acc = tmem_base + (uint32_t)as * BN;
+      tc::mbar_wait(smem_u32(&acc_empty[as]), ((uint32_t)(local >> 1) & 1u) ^ 1u);   // epilogue drained this accumulator
       tc::fence_after_sync();
-      if (tc::elect_one()) {
-        const uint32_t a_base = (tiles + (uint32_t)s * kStageBytes) >> 4;  // smem < 256 KiB: fits the 14-bit field
-        const uint32_t b_base = a_base + (uint32_t)SA * (kTileBytes >> 4);
+      for (int it = 0; it < nkb; ++it) {
+        tc::mbar_wait(smem_u32(&full_bar[s]), ph);
+        tc::fence_after_sync();
+        if (tc::elect_one()) {
+          const uint32_t a_base = (tiles + (uint32_t)s * kStageBytes) >> 4;  // smem < 256 KiB: fits the 14-bit field
+          const uint32_t b_base = a_base + (uint32_t)SA * (kTileBytes >> 4);
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
+          for (int k = 0; k < BK / 16; ++k) {
 #pragma unroll
-          for (int i = 0; i < SA; ++i) {
+            for (int i = 0; i < SA; ++i) {
 #pragma unroll
-            for (int j = 0; j < SB; ++j) {
-              if (i + j < S) {
-                const uint64_t da = kADescHi | (uint64_t)(a_base + (uint32_t)((i * kTileBytes + k * kAStep) >> 4));
-                const uint64_t db = kBDescHi | (uint64_t)(b_base + (uint32_t)((j * kTileBytes + k * kBStep) >> 4));
-                tc::mma_f16_ss(tmem_base, da, db, idesc, (k == 0 && i == 0 && j == 0) ? (uint32_t)(it > 0) : 1u);
+              for (int j = 0; j < SB; ++j) {
+                if (i + j < S) {
+                  const uint64_t da = kADescHi | (uint64_t)(a_base + (uint32_t)((i * kTileBytes + k * kAStep) >> 4));
+                  const uint64_t db = kBDescHi | (uint64_t)(b_base + (uint32_t)((j * kBTile + k * kBStep) >> 4));
+                  tc::mma_f16_ss(tmem_acc, da, db, idesc, (k == 0 && i == 0 && j == 0) ? (uint32_t)(it > 0) : 1u);
+                }
               }
             }
           }
+          tc::mma_commit(smem_u32(&empty_bar[s]));                      // stage reusable once these MMAs have read it
+          if (it == nkb - 1) tc::mma_commit(smem_u32(&acc_full[as]));   // accumulator complete
         }
-        tc::mma_commit(smem_u32(&empty_bar[s]));                      // stage reusable once these MMAs have read it
-        if (it == nkb - 1) tc::mma_commit(smem_u32(&acc_bar));        // accumulator complete
+        __syncwarp();
+        if (++s == stages) { s = 0; ph ^= 1u; }
       }
-      __syncwarp();
-      if (++s == stages) { s = 0; ph ^= 1u; }
     }
   } else {
     // ===== epilogue: warp w owns TMEM lanes [32*(w%4), +32) = output rows m0 + 32*(w%4) + lane =====
     const int q = warp & 3;
-    const int row = m0 + q * 32 + lane;
-    const bool row_ok = row < p.M;
-    tc::mbar_wait(smem_u32(&acc_bar), 0);
-    tc::fence_after_sync();
     const bool al0 = p.out0 && (p.ldo0 % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.out0) & (p.out0_dtype == PEA_F32 ? 31 : 15)) == 0);
     const bool al1 = p.out1_nsplit > 0 && (p.ldo1 % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.out1[0]) & 15) == 0) &&
                      (p.out1_nsplit < 2 || (reinterpret_cast<uintptr_t>(p.out1[1]) & 15) == 0) &&
                      (p.out1_nsplit < 3 || (reinterpret_cast<uintptr_t>(p.out1[2]) & 15) == 0);
     const bool alx = p.aux && (p.ldaux % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.aux) & (p.aux_dtype == PEA_F32 ? 31 : 15)) == 0);
+    int local = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++local) {
+    int m0, n0, kb_begin, nkb;
+    tile_coords(tile, m0, n0, kb_begin, nkb);
+    const int as = local & 1;
+    const int row = m0 + q * 32 + lane;
+    const bool row_ok = row < p.M;
     const float* radd = (p.rowadd && row_ok) ? p.rowadd + (long long)(row / p.rowadd_group) * p.N : nullptr;
+    tc::mbar_wait(smem_u32(&acc_full[as]), (uint32_t)(local >> 1) & 1u);
+    tc::fence_after_sync();
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
       uint32_t v[32];
-      tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+      tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c * 32), v);
       tc::tmem_ld_wait();
       if (!row_ok) continue;
 #pragma unroll
@@ -310,6 +341,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         }
       }
     }
+    tc::fence_before_sync();
+    __syncwarp();
+    if (lane == 0) tc::mbar_arrive(smem_u32(&acc_empty[as]));   // this accumulator may be overwritten (tile local + 2)
+    }
   }
 
   tc::fence_before_sync();
@@ -320,35 +355,39 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   }
 }
 
-template <int SA, int SB, int A_MN, int B_MN>
-int launch(const GemmParams& p, dim3 grid, size_t smem, cudaStream_t st) {
+template <int SA, int SB, int A_MN, int B_MN, int BN>
+int launch(const GemmParams& p, int ctas, size_t smem, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    PEA_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<SA, SB, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemBudget + 1024)));
+    PEA_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<SA, SB, A_MN, B_MN, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemBudget + 1024)));
     attr_set = true;
   }
-  gemm_tc_kernel<SA, SB, A_MN, B_MN><<<grid, kThreads, smem, st>>>(p);
+  gemm_tc_kernel<SA, SB, A_MN, B_MN, BN><<<ctas, kThreads, smem, st>>>(p);
   PEA_LAUNCH_CHECK();
   return PEA_OK;
 }
 
-template <int SA, int SB>
-int dispatch_major(const GemmParams& p, dim3 grid, size_t smem, cudaStream_t st) {
+template <int SA, int SB, int BN>
+int dispatch_major(const GemmParams& p, int ctas, size_t smem, cudaStream_t st) {
   switch (p.a_mn * 2 + p.b_mn) {
-    case 0: return launch<SA, SB, 0, 0>(p, grid, smem, st);
-    case 1: return launch<SA, SB, 0, 1>(p, grid, smem, st);
-    case 2: return launch<SA, SB, 1, 0>(p, grid, smem, st);
-    default: return launch<SA, SB, 1, 1>(p, grid, smem, st);
+    case 0: return launch<SA, SB, 0, 0, BN>(p, ctas, smem, st);
+    case 1: return launch<SA, SB, 0, 1, BN>(p, ctas, smem, st);
+    case 2: return launch<SA, SB, 1, 0, BN>(p, ctas, smem, st);
+    default: return launch<SA, SB, 1, 1, BN>(p, ctas, smem, st);
   }
 }
 
-int dispatch(const GemmParams& p, dim3 grid, size_t smem, cudaStream_t st) {
+// BN = 256 tiles exist for single-plane operands only (the throughput mode); the fp32-accurate plane modes use 128.
+bool has_bn256(int sa, int sb) { return sa == 1 && sb == 1; }
+
+int dispatch(const GemmParams& p, int bn, int ctas, size_t smem, cudaStream_t st) {
+  if (bn == 256) return dispatch_major<1, 1, 256>(p, ctas, smem, st);
   switch (p.sa * 4 + p.sb) {
-    case 1 * 4 + 1: return dispatch_major<1, 1>(p, grid, smem, st);
-    case 2 * 4 + 1: return dispatch_major<2, 1>(p, grid, smem, st);
-    case 1 * 4 + 2: return dispatch_major<1, 2>(p, grid, smem, st);
-    case 2 * 4 + 2: return dispatch_major<2, 2>(p, grid, smem, st);
-    case 3 * 4 + 3: return dispatch_major<3, 3>(p, grid, smem, st);
+    case 1 * 4 + 1: return dispatch_major<1, 1, 128>(p, ctas, smem, st);
+    case 2 * 4 + 1: return dispatch_major<2, 1, 128>(p, ctas, smem, st);
+    case 1 * 4 + 2: return dispatch_major<1, 2, 128>(p, ctas, smem, st);
+    case 2 * 4 + 2: return dispatch_major<2, 2, 128>(p, ctas, smem, st);
+    case 3 * 4 + 3: return dispatch_major<3, 3, 128>(p, ctas, smem, st);
   }
   set_error("gemm: plane combination (%d, %d) is not instantiated (supported: 1x1, 2x1, 1x2, 2x2, 3x3)", p.sa, p.sb);
   return PEA_EUNSUPPORTED;
@@ -412,6 +451,11 @@ extern "C" int pea_gemm(const pea_gemm_desc* g, void* stream) {
   p.sa = g->nsplit_a; p.sb = g->nsplit_b;
   p.a_mn = g->a_kmajor ? 0 : 1; p.b_mn = g->b_kmajor ? 0 : 1;
   const bool fp16 = g->in_dtype == PEA_F16;
+  // 128 x 256 tiles when that still leaves at least one tile per SM (halves A re-reads, 2/3 instead of 1/2 tensor duty
+  // under the shared-memory bandwidth bound); otherwise 128 x 128 for parallelism.
+  const int m_tiles = (g->M + BM - 1) / BM;
+  int bn = 128;
+  if (has_bn256(p.sa, p.sb) && g->split_k <= 1 && (long long)m_tiles * ((g->N + 255) / 256) >= num_sms()) bn = 256;
   for (int i = 0; i < p.sa; ++i) {
     PEA_CHECK_ARG(g->d_A[i] && (reinterpret_cast<uintptr_t>(g->d_A[i]) & 15) == 0, "gemm: A plane %d null or not 16-byte aligned", i);
     const uint64_t dims[2] = {(uint64_t)(p.a_mn ? g->M : g->K), (uint64_t)(p.a_mn ? g->K : g->M)};
@@ -424,7 +468,7 @@ extern "C" int pea_gemm(const pea_gemm_desc* g, void* stream) {
     PEA_CHECK_ARG(g->d_B[j] && (reinterpret_cast<uintptr_t>(g->d_B[j]) & 15) == 0, "gemm: B plane %d null or not 16-byte aligned", j);
     const uint64_t dims[2] = {(uint64_t)(p.b_mn ? g->N : g->K), (uint64_t)(p.b_mn ? g->K : g->N)};
     const uint64_t str[1] = {(uint64_t)g->ldb * 2};
-    const uint32_t box[2] = {64u, p.b_mn ? 64u : 128u};
+    const uint32_t box[2] = {64u, p.b_mn ? 64u : (uint32_t)bn};
     int rc = encode_tmap_16bit(&p.tmB[j], g->d_B[j], 2, dims, str, box, fp16);
     if (rc != PEA_OK) return rc;
   }
@@ -437,12 +481,15 @@ extern "C" int pea_gemm(const pea_gemm_desc* g, void* stream) {
   }
   p.kb_per_split = (p.kb_total + splits - 1) / splits;
   splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;  // no empty split
-  const size_t stage_bytes = (size_t)(p.sa + p.sb) * kTileBytes;
+  p.m_tiles = m_tiles;
+  p.n_tiles = (g->N + bn - 1) / bn;
+  p.splits = splits;
+  p.total_tiles = p.m_tiles * p.n_tiles * splits;
+  const size_t stage_bytes = (size_t)p.sa * kTileBytes + (size_t)p.sb * bn * BK * 2;
   int stages = (int)(kSmemBudget / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
-  if (stages > p.kb_per_split) stages = p.kb_per_split < 1 ? 1 : p.kb_per_split;
   p.stages = stages;
-  p.idesc = tc::make_idesc(fp16 ? 0 : 1, BM, BN, p.a_mn, p.b_mn);
+  p.idesc = tc::make_idesc(fp16 ? 0 : 1, BM, bn, p.a_mn, p.b_mn);
   p.alpha = g->alpha;
   p.bias = g->d_bias;
   p.aux = g->d_aux; p.aux_dtype = g->aux_dtype; p.ldaux = g->ldaux;
@@ -457,6 +504,6 @@ extern "C" int pea_gemm(const pea_gemm_desc* g, void* stream) {
   p.out1_nsplit = g->out1_nsplit; p.out1_dtype = g->out1_dtype; p.ldo1 = g->ldo1;
 
   const size_t smem = (size_t)stages * stage_bytes + 1024;
-  dim3 grid((g->N + BN - 1) / BN, (g->M + BM - 1) / BM, splits);
-  return dispatch(p, grid, smem, static_cast<cudaStream_t>(stream));
+  const int ctas = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+  return dispatch(p, bn, ctas, smem, static_cast<cudaStream_t>(stream));
 }

@@ -30,8 +30,11 @@ def timeit(fn, iters, warm=None):
         fn()
     ts = []
     for _ in range(iters):
-        scratch.view(torch.int32).sum()  # L2 flush by READING 256 MB: leaves clean lines (a fill would leave 126 MB of dirty
-        #                                    lines whose write-back is then charged to the kernel under test)
+        if os.environ.get("PEA_MB_FLUSH") == "fill":
+            scratch.fill_(1)
+        else:
+            scratch.view(torch.int32).sum()  # L2 flush by READING 256 MB: leaves clean lines (a fill leaves 126 MB of
+            #                                    dirty lines whose write-back is then charged to the kernel under test)
         torch.cuda._sleep(600000)  # ~0.3 ms of GPU spin so the host is ahead of the GPU when the timed launch is enqueued
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); fn(); e1.record()
