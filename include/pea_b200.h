@@ -150,6 +150,18 @@ int pea_colsum_accum(const void* d_x, pea_dtype x_dtype, int M, int N, long long
 int pea_cfg_select(const unsigned char* d_mask, const void* d_uncond, const void* d_cond, void* d_out, int B,
                    long long row_elems, pea_dtype dtype, void* stream);
 
+/* ----------------------------------------------------------------------------------------------------------
+ * Input side of the step: offset noise + DDPM add_noise + cast in one pass.
+ * Replaces train_sdxl_zh.py:311-323 (train_sd_zh.py:157-169):
+ *     noise  = noise_raw + noise_offset * offs[b, c]                     (offs ~ N(0,1) of shape [B, C, 1, 1])
+ *     noisy  = sqrt(acp[t_b]) * latents + sqrt(1 - acp[t_b]) * noise     (DDPMScheduler.add_noise)
+ * latents [B, C, HW] any float dtype; noise_raw / offs fp32; acp = alphas_cumprod fp32 [T]; t int64 [B];
+ * outputs d_noise, d_noisy in out_dtype (the UNet dtype).
+ * -------------------------------------------------------------------------------------------------------- */
+int pea_add_noise(const void* d_latents, pea_dtype lat_dtype, const float* d_noise_raw, const float* d_offs, float noise_offset,
+                  const float* d_acp, int T, const long long* d_t, int B, int C, long long HW, void* d_noise, void* d_noisy,
+                  pea_dtype out_dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -118,6 +118,20 @@ def cfg_select(prompt_mask: Tensor, ctx_uncond: Tensor, ctx_cond: Tensor) -> Ten
 
 
 # =============================================================================
+# N4 -- input side: offset noise + DDPM add_noise (train_sdxl_zh.py:311-323)
+# =============================================================================
+def add_noise(latents: Tensor, noise_raw: Tensor, offs: Tensor, noise_offset: float, alphas_cumprod: Tensor, timesteps: Tensor,
+              unet_dtype: torch.dtype) -> Tuple[Tensor, Tensor]:
+    """``noise = randn + noise_offset * randn(B, C, 1, 1)`` (:311-315), cast to the UNet dtype (:317), then diffusers'
+    ``DDPMScheduler.add_noise``: ``sqrt(acp[t]) * latents + sqrt(1 - acp[t]) * noise`` (:322), cast (:323)."""
+    noise = (noise_raw + noise_offset * offs.view(offs.shape[0], offs.shape[1], 1, 1)).to(unet_dtype)
+    a = alphas_cumprod.to(torch.float32)[timesteps]
+    sa, sb = a.sqrt().view(-1, 1, 1, 1), (1 - a).sqrt().view(-1, 1, 1, 1)
+    noisy = (sa * latents.float() + sb * noise.float()).to(unet_dtype)
+    return noise, noisy
+
+
+# =============================================================================
 # A5 / A6 -- attn2 (diffusers AttnProcessor2_0 restated; reference call sites train_sdxl_zh.py:397,415)
 # =============================================================================
 def attn2_core(q: Tensor, k: Tensor, v: Tensor, heads: int, explicit: bool = False) -> Tensor:

@@ -91,6 +91,8 @@ SYMBOLS = {
                                    C.c_int, C.c_void_p]),
     "pea_mean_tokens": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "pea_colsum_accum": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_void_p, C.c_void_p]),
+    "pea_add_noise": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                                C.c_int, C.c_longlong, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "pea_cfg_select": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_int, C.c_void_p]),
 }
 

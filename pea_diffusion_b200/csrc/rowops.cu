@@ -166,10 +166,41 @@ __global__ void cfg_select_kernel(const unsigned char* __restrict__ mask, const 
     out[base + i] = src[base + i];
 }
 
+__global__ void add_noise_kernel(const void* __restrict__ lat, pea_dtype ldt, const float* __restrict__ raw, const float* __restrict__ offs,
+                                 float noise_offset, const float* __restrict__ acp, int T, const long long* __restrict__ t, int C,
+                                 long long HW, void* __restrict__ noise, void* __restrict__ noisy, pea_dtype odt) {
+  const int b = blockIdx.z, c = blockIdx.y;
+  long long ts = t[b];
+  ts = ts < 0 ? 0 : (ts >= T ? T - 1 : ts);
+  const float a = acp[ts];
+  const float sa = sqrtf(a), sb = sqrtf(1.0f - a);
+  const float off = offs ? noise_offset * offs[(long long)b * C + c] : 0.f;
+  const long long base = ((long long)b * C + c) * HW;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += (long long)gridDim.x * blockDim.x) {
+    // the reference rounds the noise to the UNet dtype BEFORE add_noise (train_sdxl_zh.py:317): do the same
+    float n = raw[base + i] + off;
+    store_any(noise, odt, base + i, n);
+    n = load_any(noise, odt, base + i);
+    store_any(noisy, odt, base + i, sa * load_any(lat, ldt, base + i) + sb * n);
+  }
+}
+
 }  // namespace
 }  // namespace pea
 
 using namespace pea;
+
+extern "C" int pea_add_noise(const void* d_latents, pea_dtype lat_dtype, const float* d_noise_raw, const float* d_offs, float noise_offset,
+                             const float* d_acp, int T, const long long* d_t, int B, int C, long long HW, void* d_noise, void* d_noisy,
+                             pea_dtype out_dtype, void* stream) {
+  PEA_CHECK_ARG(d_latents && d_noise_raw && d_acp && d_t && d_noise && d_noisy, "add_noise: null pointer");
+  PEA_CHECK_ARG(B >= 1 && C >= 1 && HW >= 1 && T >= 1 && C <= 65535 && B <= 65535, "add_noise: bad shape");
+  const int gx = (int)((HW + 255) / 256 < 64 ? (HW + 255) / 256 : 64);
+  add_noise_kernel<<<dim3(gx, C, B), 256, 0, (cudaStream_t)stream>>>(d_latents, lat_dtype, d_noise_raw, d_offs, noise_offset, d_acp, T,
+                                                                    d_t, C, HW, d_noise, d_noisy, out_dtype);
+  PEA_LAUNCH_CHECK();
+  return PEA_OK;
+}
 
 extern "C" int pea_layernorm_fwd(const void* d_x, pea_dtype x_dtype, const float* d_gamma, const float* d_beta, int M, int D,
                                  float eps, void* const d_y_planes[3], int nsplit, pea_dtype plane_dtype, float* d_mean,

@@ -190,6 +190,25 @@ def cfg_select(mask_u8: Tensor, uncond: Tensor, cond: Tensor) -> Tensor:
     return out
 
 
+def add_noise(latents: Tensor, noise_raw: Tensor, offs: Optional[Tensor], noise_offset: float, alphas_cumprod: Tensor,
+              timesteps: Tensor, out_dtype: torch.dtype):
+    """Offset noise + DDPM add_noise + cast (train_sdxl_zh.py:311-323) -> (noise, noisy_latents) in ``out_dtype``."""
+    require_cuda(latents, noise_raw, offs, alphas_cumprod, timesteps)
+    B, Cc = latents.shape[:2]
+    HW = latents.numel() // (B * Cc)
+    latents = latents.contiguous()
+    noise_raw = noise_raw.to(torch.float32).contiguous()
+    offs_c = None if offs is None else offs.to(torch.float32).reshape(B, Cc).contiguous()
+    acp = alphas_cumprod.to(torch.float32).contiguous()
+    t = timesteps.to(torch.int64).contiguous()
+    noise = torch.empty(latents.shape, device=latents.device, dtype=out_dtype)
+    noisy = torch.empty(latents.shape, device=latents.device, dtype=out_dtype)
+    check(lib.pea_add_noise(latents.data_ptr(), dtype_code(latents.dtype), noise_raw.data_ptr(), ptr(offs_c), float(noise_offset),
+                            acp.data_ptr(), acp.numel(), t.data_ptr(), B, Cc, HW, noise.data_ptr(), noisy.data_ptr(),
+                            dtype_code(out_dtype), stream_ptr(latents.device)), "pea_add_noise")
+    return noise, noisy
+
+
 def attn2_fwd(q: Tensor, kv: Tensor, heads: int, scale: float) -> Tensor:
     """q [B,N,C], kv [B,L,2C] (K in columns [0,C), V in [C,2C)) -> o [B,N,C] = softmax(q k^T scale) v per head."""
     require_cuda(q, kv)
