@@ -58,6 +58,138 @@ class _Attn2Fn(torch.autograd.Function):
         return (dq if ctx_.needs_input_grad[0] else None), dctx, None, None, None, None
 
 
+class _ProjectAllFn(torch.autograd.Function):
+    """context [B,L,Dc] -> (K|V of EVERY attn2 layer of the UNet as one [B*L, sum(2C)] tensor, gradient token).
+
+    One GEMM against the concatenation of all layers' [Wk; Wv] replaces 70 (SDXL) one-wave GEMMs per UNet forward, and
+    its backward forms dContext = dKV_all @ Wcat_all as ONE split-K GEMM instead of 70 GEMMs + 69 accumulations.  The
+    per-layer attention backward kernels add their dK|dV straight into column slices of ``group.dkv_all``; the 1-element
+    ``token`` output is consumed only by the FIRST attn2 layer of the forward pass, whose backward is the last attn2
+    backward to run (every other attn2 layer is downstream of it), so autograd calls this node's backward exactly when
+    ``dkv_all`` is complete."""
+
+    @staticmethod
+    def forward(ctx_, context: Tensor, group: "Attn2Group"):
+        B, L, Dc = context.shape
+        wcat = group.weights(context.dtype, context.device)
+        kv_all = torch.empty(B * L, group.total, device=context.device, dtype=context.dtype)
+        ops.gemm([context.reshape(B * L, Dc)], [wcat], B * L, group.total, Dc, out0=kv_all)
+        ctx_.group, ctx_.shape, ctx_.dtype = group, (B, L, Dc), context.dtype
+        group.dkv_all = None
+        group.bwd_calls = 0
+        if ctx_.needs_input_grad[0]:
+            group.dkv_all = torch.zeros(B, L, group.total, device=context.device, dtype=torch.float32)
+        token = context.new_zeros(1)
+        ctx_.mark_non_differentiable(kv_all)
+        return kv_all, token
+
+    @staticmethod
+    def backward(ctx_, _g_kv, g_token):
+        group = ctx_.group
+        B, L, Dc = ctx_.shape
+        if group.bwd_calls != group.fwd_calls_with_grad:
+            raise RuntimeError(f"attn2 group: dContext requested after {group.bwd_calls} of {group.fwd_calls_with_grad} layer "
+                               "backwards -- the first attn2 layer is not upstream of all others in this network")
+        wcat = group.weights(ctx_.dtype, group.dkv_all.device)
+        dkv16 = ops.split_planes(group.dkv_all.view(B * L, group.total), 1, ctx_.dtype)
+        dctx = torch.zeros(B * L, Dc, device=wcat.device, dtype=torch.float32)
+        kb = (group.total + 63) // 64
+        tiles = ((B * L + 127) // 128) * ((Dc + 127) // 128)
+        split = max(1, min(kb // 8, (4 * group.sms + tiles - 1) // tiles))
+        ops.gemm(dkv16, [wcat], B * L, Dc, group.total, b_kmajor=False, out0=dctx, accumulate=True, split_k=split)
+        group.dkv_all = None
+        return dctx.view(B, L, Dc).to(ctx_.dtype), None
+
+
+class _Attn2GroupedFn(torch.autograd.Function):
+    """One layer's attention core on its column slice of the group's K|V tensor."""
+
+    @staticmethod
+    def forward(ctx_, q: Tensor, token: Optional[Tensor], kv: Tensor, group: "Attn2Group", layer: int, heads: int, scale: float):
+        o = ops.attn2_fwd(q, kv, heads, scale)
+        ctx_.save_for_backward(q, kv)
+        ctx_.group, ctx_.layer, ctx_.heads, ctx_.scale, ctx_.has_token = group, layer, heads, scale, token is not None
+        ctx_.track = group.dkv_all is not None
+        if ctx_.track:
+            group.fwd_calls_with_grad += 1
+        return o
+
+    @staticmethod
+    def backward(ctx_, do: Tensor):
+        q, kv = ctx_.saved_tensors
+        group = ctx_.group
+        dkv = None
+        if ctx_.track:
+            off, c2 = group.offsets[ctx_.layer], group.widths[ctx_.layer]
+            dkv = group.dkv_all[:, :, off:off + c2]
+        dq, _ = ops.attn2_bwd(q, kv, do, ctx_.heads, ctx_.scale, dkv=dkv)
+        if ctx_.track:
+            group.bwd_calls += 1
+        return (dq if ctx_.needs_input_grad[0] else None), (do.new_zeros(1) if ctx_.has_token else None), None, None, None, None, None
+
+
+class Attn2Group:
+    """All ``attn2`` modules of one UNet, in forward-call order: owns the concatenated projection weights and, per
+    forward pass, the projected context of every layer."""
+
+    def __init__(self, attns):
+        self.attns = list(attns)
+        self.widths = [2 * a.to_k.weight.shape[0] for a in self.attns]
+        self.offsets = [0]
+        for w in self.widths[:-1]:
+            self.offsets.append(self.offsets[-1] + w)
+        self.total = sum(self.widths)
+        self.index = {id(a): i for i, a in enumerate(self.attns)}
+        self._wcat: Optional[Tensor] = None
+        self._wkey = None
+        self._ctx_ref: Optional[Tensor] = None     # strong reference: identity is the cache key (no address reuse)
+        self._ctx_key = None
+        self._kv_all: Optional[Tensor] = None
+        self._token: Optional[Tensor] = None
+        self.dkv_all: Optional[Tensor] = None
+        self.fwd_calls_with_grad = 0
+        self.bwd_calls = 0
+        self.sms = torch.cuda.get_device_properties(0).multi_processor_count if torch.cuda.is_available() else 148
+
+    def weights(self, dtype, device) -> Tensor:
+        key = (dtype, device, tuple(a.to_k.weight._version for a in self.attns), tuple(a.to_v.weight._version for a in self.attns),
+               self.attns[0].to_k.weight.data_ptr())
+        if self._wcat is None or self._wkey != key:
+            parts = []
+            for a in self.attns:
+                parts += [a.to_k.weight.detach(), a.to_v.weight.detach()]
+            self._wcat = torch.cat(parts, dim=0).to(device=device, dtype=dtype).contiguous()
+            self._wkey = key
+        return self._wcat
+
+    def supported(self, dtype) -> bool:
+        dc = self.attns[0].to_k.weight.shape[1]
+        return all(a.to_k.weight.shape[1] == dc and getattr(a.to_k, "lora_layer", None) is None and
+                   getattr(a.to_v, "lora_layer", None) is None for a in self.attns) and dc % 8 == 0
+
+    def project(self, context: Tensor, dtype):
+        """-> (kv_all [B*L, total], token or None) for the context tensor OBJECT the UNet passed down.  Recomputed when
+        a different tensor (or an in-place modified one, a different dtype or grad mode) arrives; otherwise the
+        pass's -- or, for a denoise loop that keeps feeding the same tensor, the loop's -- projection is reused."""
+        need_grad = torch.is_grad_enabled() and context.requires_grad
+        key = (context._version, dtype, need_grad)
+        if self._ctx_ref is context and self._ctx_key == key and self._kv_all is not None:
+            tok, self._token = self._token, None     # only the first layer of a pass carries the token
+            return self._kv_all, tok
+        ctx = context.to(dtype)
+        if not ctx.is_contiguous():
+            ctx = ctx.contiguous()
+        self.fwd_calls_with_grad = 0
+        kv_all, token = _ProjectAllFn.apply(ctx, self)
+        self._ctx_ref, self._ctx_key = context, key
+        self._kv_all = kv_all
+        self._token = None
+        return kv_all, (token if need_grad else None)
+
+    def release(self) -> None:
+        self._ctx_ref = self._kv_all = self._token = self.dkv_all = None
+
+
 def attn2_core(q: Tensor, context: Tensor, wkv: Tensor, heads: int, scale: Optional[float] = None,
                kv: Optional[Tensor] = None) -> Tensor:
     """Functional form: softmax(q (ctx Wk^T)^T * scale) (ctx Wv^T) with ``wkv = cat([Wk, Wv], 0)``."""
@@ -76,9 +208,10 @@ class PEAAttn2Processor:
     every step (tests/test_sdxl_zh.py:378-391) projects it once instead of once per step -- forward-only use.
     """
 
-    def __init__(self, fallback=None, cache_kv: bool = False):
+    def __init__(self, fallback=None, cache_kv: bool = False, group: Optional[Attn2Group] = None):
         self.fallback = fallback
         self.cache_kv = cache_kv
+        self.group = group
         self._wkv: Optional[Tensor] = None
         self._wkv_key = None
         self._kv: Optional[Tensor] = None
@@ -118,14 +251,26 @@ class PEAAttn2Processor:
                                  attention_mask=attention_mask, temb=temb, scale=scale)
         ops.require_cuda(hidden_states, encoder_hidden_states)
         dt = hidden_states.dtype
+        q = attn.to_q(hidden_states)
+        if self.group is not None and id(attn) in self.group.index and self.group.supported(dt):
+            # all layers' K|V from ONE projection GEMM per forward pass (and per denoise loop when the context is reused)
+            B, L, _ = encoder_hidden_states.shape
+            kv_all, token = self.group.project(encoder_hidden_states, dt)
+            i = self.group.index[id(attn)]
+            off, c2 = self.group.offsets[i], self.group.widths[i]
+            kv = kv_all.view(B, L, self.group.total)[:, :, off:off + c2]
+            o = _Attn2GroupedFn.apply(q, token, kv, self.group, i, attn.heads, float(attn.scale))
+            o = attn.to_out[0](o)
+            return attn.to_out[1](o)
         context = encoder_hidden_states.to(dt)
         if not context.is_contiguous():
             context = context.contiguous()
-        q = attn.to_q(hidden_states)
         wkv = self._weights(attn, dt)
         kv = None
         if self.cache_kv and not (torch.is_grad_enabled() and context.requires_grad):
-            key = (context.data_ptr(), context._version, tuple(context.shape), dt)
+            # identity of the context TENSOR OBJECT (held strongly, so its address cannot be recycled) + its version
+            key = (id(encoder_hidden_states), encoder_hidden_states._version, tuple(context.shape), dt)
+            self._kv_ctx = encoder_hidden_states
             if self._kv is None or self._kv_key != key:
                 B, L, Dc = context.shape
                 self._kv = torch.empty(B, L, wkv.shape[0], device=q.device, dtype=dt)
@@ -137,18 +282,27 @@ class PEAAttn2Processor:
         return attn.to_out[1](o)
 
 
-def install(unet, freeze: bool = True, cache_kv: bool = False) -> Dict[str, object]:
+def install(unet, freeze: bool = True, cache_kv: bool = False, group_projection: bool = True) -> Dict[str, object]:
     """``unet.set_attn_processor({...})`` with ``PEAAttn2Processor`` on every ``*.attn2`` module and the existing
     processor kept everywhere else (diffusers requires the dict to cover every attention module).
 
-    ``freeze=True`` also marks the UNet's parameters ``requires_grad_(False)``: the reference hands only the adapter's
+    ``group_projection=True`` (default) projects the context for ALL attn2 layers with one GEMM per forward pass (and
+    forms dContext with one split-K GEMM per backward pass); with ``cache_kv`` the projection also survives across
+    passes while the same context tensor is fed (denoise loops).  ``freeze=True`` also marks the UNet's parameters ``requires_grad_(False)``: the reference hands only the adapter's
     parameters to the optimizer (train_sdxl_zh.py:166-168) yet lets autograd form and discard every UNet weight
     gradient; skipping them does not change any result.
     """
     current = dict(unet.attn_processors)
+    group = None
+    if group_projection:
+        # attn2 modules in registration (= forward-call) order; one projection GEMM per pass serves all of them
+        mods = dict(unet.named_modules())
+        attns = [mods[name[:-len(".processor")]] for name in current if name.endswith("attn2.processor")]
+        if attns and len({a.to_k.weight.shape[1] for a in attns}) == 1:
+            group = Attn2Group(attns)
     procs = {}
     for name, proc in current.items():
-        procs[name] = PEAAttn2Processor(fallback=proc, cache_kv=cache_kv) if name.endswith("attn2.processor") else proc
+        procs[name] = PEAAttn2Processor(fallback=proc, cache_kv=cache_kv, group=group) if name.endswith("attn2.processor") else proc
     unet.set_attn_processor(procs)
     if freeze:
         unet.requires_grad_(False)

@@ -223,20 +223,24 @@ def attn2_fwd(q: Tensor, kv: Tensor, heads: int, scale: float) -> Tensor:
     return o
 
 
-def attn2_bwd(q: Tensor, kv: Tensor, do: Tensor, heads: int, scale: float):
-    """-> (dq [B,N,C] in q's dtype, dkv [B,L,2C] fp32)."""
-    require_cuda(q, kv, do)
+def attn2_bwd(q: Tensor, kv: Tensor, do: Tensor, heads: int, scale: float, dkv: Optional[Tensor] = None):
+    """-> (dq [B,N,C] in q's dtype, dkv [B,L,2C] fp32).  ``dkv`` may be a caller-owned fp32 [B,L,2C] view (unit column
+    stride) that is ACCUMULATED into -- e.g. one layer's column slice of a buffer shared by all layers."""
+    require_cuda(q, kv, do, dkv)
     B, N, Cq = q.shape
     L = kv.shape[1]
     if do.stride(-1) != 1 or do.stride(1) % 8 != 0 or do.stride(0) != N * do.stride(1):
         do = do.contiguous()
     dq = torch.empty(B, N, Cq, device=q.device, dtype=q.dtype)
-    dkv = torch.zeros(B, L, 2 * Cq, device=q.device, dtype=torch.float32)
+    if dkv is None:
+        dkv = torch.zeros(B, L, 2 * Cq, device=q.device, dtype=torch.float32)
+    elif dkv.dtype != torch.float32 or tuple(dkv.shape) != (B, L, 2 * Cq) or dkv.stride(2) != 1:
+        raise ValueError("attn2_bwd: dkv must be an fp32 [B, L, 2C] view with unit column stride")
     d = _attn_desc(q, kv, heads, scale)
     d.d_do, d.ld_do = do.data_ptr(), do.stride(1)
     d.d_dq, d.ld_dq = dq.data_ptr(), Cq
     d.d_dk, d.d_dv = dkv.data_ptr(), dkv.data_ptr() + 4 * Cq
-    d.ld_dkv, d.bs_dkv = 2 * Cq, L * 2 * Cq
+    d.ld_dkv, d.bs_dkv = dkv.stride(1), dkv.stride(0)
     es = q.element_size()
     # SURVEY.md section 8d: read Q, dO, write dQ; read K, V; accumulate dK, dV (fp32 here: 2 * 4 bytes)
     with _timed("attn2_bwd", 3 * B * N * Cq * es + 2 * B * L * Cq * es + 2 * B * L * Cq * 4, 10 * B * N * L * Cq):
