@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--adapter-precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager step instead of the CUDA-graph replay")
+    ap.add_argument("--timed-only", action="store_true", help="skip the eager per-kernel pass and the e2e loop (ncu launch-list runs)")
     ap.add_argument("--tiny", action="store_true", help="tiny shell (debug only; the JSON line says so)")
     return ap.parse_args()
 
@@ -260,7 +261,7 @@ def main():
     ops.TIMER.enabled = False
     launches = _lib.launch_count() - n0
     prof_steps = args.steps
-    if graph_mode:
+    if graph_mode and not args.timed_only:
         # A graph replay re-launches the kernels the capture recorded (launch_count only sees the capture), and CUDA
         # events cannot bracket nodes inside a graph: run the SAME step eagerly for the per-kernel roofline figures and
         # for the launch count.
@@ -290,8 +291,11 @@ def main():
         out = trainer.step(to_device(hbatch, dev))
         host_loss.copy_(out, non_blocking=False)  # D2H read of the step's result (blocks like .item() would)
 
-    e2e_step()
-    ms_e2e = timed(e2e_step, args.steps)
+    if args.timed_only:
+        ms_e2e = ms_step
+    else:
+        e2e_step()
+        ms_e2e = timed(e2e_step, args.steps)
     clk = clocks.stop() if clocks else None
     h2d = sum(v.numel() * v.element_size() for v in hbatch.values())
 

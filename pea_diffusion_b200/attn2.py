@@ -146,6 +146,7 @@ class Attn2Group:
         self._ctx_key = None
         self._kv_all: Optional[Tensor] = None
         self._token: Optional[Tensor] = None
+        self._supported: Optional[bool] = None
         self.dkv_all: Optional[Tensor] = None
         self.fwd_calls_with_grad = 0
         self.bwd_calls = 0
@@ -163,9 +164,14 @@ class Attn2Group:
         return self._wcat
 
     def supported(self, dtype) -> bool:
-        dc = self.attns[0].to_k.weight.shape[1]
-        return all(a.to_k.weight.shape[1] == dc and getattr(a.to_k, "lora_layer", None) is None and
-                   getattr(a.to_v, "lora_layer", None) is None for a in self.attns) and dc % 8 == 0
+        """LoRA layers on any to_k / to_v send the whole group back to the per-layer path (checked once per pass: the
+        first layer's call; the answer is cached until the next projection)."""
+        if self._supported is None:
+            dc = self.attns[0].to_k.weight.shape[1]
+            self._supported = dc % 8 == 0 and all(
+                a.to_k.weight.shape[1] == dc and getattr(a.to_k, "lora_layer", None) is None and
+                getattr(a.to_v, "lora_layer", None) is None for a in self.attns)
+        return self._supported
 
     def project(self, context: Tensor, dtype):
         """-> (kv_all [B*L, total], token or None) for the context tensor OBJECT the UNet passed down.  Recomputed when
@@ -179,6 +185,7 @@ class Attn2Group:
         ctx = context.to(dtype)
         if not ctx.is_contiguous():
             ctx = ctx.contiguous()
+        self._supported = None       # re-validated by the next pass
         self.fwd_calls_with_grad = 0
         kv_all, token = _ProjectAllFn.apply(ctx, self)
         self._ctx_ref, self._ctx_key = context, key

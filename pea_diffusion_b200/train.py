@@ -206,7 +206,7 @@ class KDTrainer:
         torch.cuda.current_stream().wait_stream(side)
         self.opt.zero_grad(set_to_none=True)
         self._graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self._graph):
+        with torch.cuda.graph(self._graph, stream=side):   # same stream as the warm-up: AccumulateGrad nodes stay put
             self._static_out = self._forward_backward(self._static_in)
 
     def step(self, batch: Mapping[str, Tensor]) -> Tensor:
