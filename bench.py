@@ -202,6 +202,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # stdout carries exactly ONE JSON line: NCCL's banner / debug output (stdout by default) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     from pea_diffusion_b200 import _lib, adapter as A, attn2, ops
