@@ -15,6 +15,7 @@ Reference call path: ``train_sdxl_zh.py:397`` (student, a
 """
 from __future__ import annotations
 
+import warnings
 from typing import Dict, Optional
 
 import torch
@@ -215,6 +216,8 @@ class PEAAttn2Processor:
     every step (tests/test_sdxl_zh.py:378-391) projects it once instead of once per step -- forward-only use.
     """
 
+    _warned = False
+
     def __init__(self, fallback=None, cache_kv: bool = False, group: Optional[Attn2Group] = None):
         self.fallback = fallback
         self.cache_kv = cache_kv
@@ -252,6 +255,10 @@ class PEAAttn2Processor:
     def __call__(self, attn, hidden_states: Tensor, encoder_hidden_states: Optional[Tensor] = None,
                  attention_mask: Optional[Tensor] = None, temb: Optional[Tensor] = None, scale: float = 1.0) -> Tensor:
         if not self._supported(attn, hidden_states, encoder_hidden_states, attention_mask):
+            if encoder_hidden_states is not None and hidden_states.is_cuda and not PEAAttn2Processor._warned:
+                PEAAttn2Processor._warned = True   # never silent: a cross-attention call is leaving the fused kernels
+                warnings.warn("PEAAttn2Processor: cross-attention call outside the fused kernel's contract (mask / LoRA on "
+                              f"to_k,to_v / > {MAX_KEYS} keys / head size / dtype {hidden_states.dtype}); using the stock processor")
             if self.fallback is None:
                 raise ops._lib.PeaError("PEAAttn2Processor: call outside the fused kernel's contract and no fallback processor set")
             return self.fallback(attn, hidden_states, encoder_hidden_states=encoder_hidden_states,
