@@ -186,12 +186,32 @@ def run_reference(args):
                        "l2": "working set >> L2"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------- our arm
+_REAL_STDOUT = None
+
+
+def _guard_stdout():
+    """stdout must carry exactly ONE JSON line.  Libraries print there too (NCCL's version banner, warnings from child
+    threads): point fd 1 at stderr for the whole run and keep a private handle on the real stdout for the JSON line."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
     args = parse()
+    _guard_stdout()
     if args.impl == "reference":
         run_reference(args)
         return
@@ -347,7 +367,7 @@ def main():
                                               f"divided by {scale:.0f} (token ratio to {latent}x{latent})"}
         except Exception as e:  # the GPU numbers stand on their own
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
