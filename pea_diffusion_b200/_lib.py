@@ -13,7 +13,7 @@ from typing import Optional, Sequence
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpea_b200.so")
+LIB_PATH = os.environ.get("PEA_B200_LIB") or os.path.join(_HERE, "libpea_b200.so")   # override: instrumented debug builds
 
 PEA_F32, PEA_F16, PEA_BF16 = 0, 1, 2
 KD_MAX_TAPS = 16

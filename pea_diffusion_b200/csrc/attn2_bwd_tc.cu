@@ -65,6 +65,15 @@ __device__ __forceinline__ void st_shared16(uint32_t addr, uint32_t a, uint32_t 
   asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
+// Optional per-tile event timeline of CTA 0 (build with -DPEA_TRACE, read with tools/trace_bwd.py): how the round-1
+// bottleneck analysis in DESIGN.md section 4.2 was obtained.  Expands to nothing in the product build.
+#ifdef PEA_TRACE
+__device__ unsigned long long g_trace[16 * 64 * 16];   // [role][tile][event]
+#define TRACE(role, tile, ev) do { if (blockIdx.x == 0 && (tile) < 64 && lane == 0) g_trace[((role) * 64 + (tile)) * 16 + (ev)] = clock64(); } while (0)
+#else
+#define TRACE(role, tile, ev) do { } while (0)
+#endif
+
 template <typename T>
 __global__ void __launch_bounds__(kThreads, 1) attn2_bwd_tc_kernel(const __grid_constant__ BwdParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -124,6 +133,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_bwd_tc_kernel(const __grid_
       }
       const int s = t % kRing;
       tc::mbar_wait(smem_u32(&ring_empty[s]), ((uint32_t)(t / kRing) & 1u) ^ 1u);
+      TRACE(0, t, 0);
       if (tc::elect_one()) {
         const uint32_t fb = smem_u32(&ring_full[s]);
         tc::mbar_expect_tx(fb, 2 * kTile);
@@ -150,7 +160,9 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_bwd_tc_kernel(const __grid_
         ++s_kvn;
       }
       const int kb = (s_kvn - 1) & 1, rs = t % kRing, g = t & 1;
+      TRACE(1, t, 0);
       tc::mbar_wait(smem_u32(&ring_full[rs]), (uint32_t)(t / kRing) & 1u);
+      TRACE(1, t, 1);
       tc::fence_after_sync();
       if (tc::elect_one()) {
         const uint32_t qa = (smem + kOffRing + rs * 2 * kTile) >> 4, doa = qa + (kTile >> 4);
@@ -175,8 +187,11 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_bwd_tc_kernel(const __grid_
       const int kb = (m_kvn - 1) & 1;
       const bool last_tile = t + 1 == ntiles;
       const bool last_of_bh = !last_tile && ((item0 + t + 1) / tpb != bh);
+      TRACE(1, t, 2);
       tc::mbar_wait(smem_u32(&ds_ready[g]), (uint32_t)(t >> 1) & 1u);
+      TRACE(1, t, 3);
       if (t > 0) tc::mbar_wait(smem_u32(&dq_free), (uint32_t)(t - 1) & 1u);            // dQ TMEM drained by tile t-1's epilogue
+      TRACE(1, t, 4);
       if (first_of_bh && flushes > 0) tc::mbar_wait(smem_u32(&dkv_free), (uint32_t)(flushes - 1) & 1u);  // dK/dV TMEM drained
       tc::fence_after_sync();
       if (tc::elect_one()) {
@@ -230,7 +245,9 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_bwd_tc_kernel(const __grid_
       }
       const int b = bh / p.H, h = bh - b * p.H;
       (void)cur_bh;
+      TRACE(2 + g, t, 0);
       tc::mbar_wait(smem_u32(&sdp_full[g]), (uint32_t)(t >> 1) & 1u);
+      TRACE(2 + g, t, 1);
       tc::fence_after_sync();
 
       // Columns >= L hold S = 0 (K rows beyond L are zero-filled), never NaN: only the chunk that straddles L needs
@@ -247,17 +264,19 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_bwd_tc_kernel(const __grid_
         tc::tmem_ld16(t_s + 0, c0); tc::tmem_ld16(t_s + 16, c1); tc::tmem_ld16(t_s + 32, c2);
         tc::tmem_ld16(t_s + 48, c3); tc::tmem_ld16(t_s + 64, c4);
         tc::tmem_ld_wait();
-        float m = -INFINITY;
+        // four independent chains: a single softmax warp per scheduler cannot hide a serial 80-long dependency chain
+        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
         for (int c = 0; c < kLP / 16; ++c) {
           if ((c + 1) * 16 <= L) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) m = fmaxf(m, __uint_as_float(sv[c * 16 + j]));
+            for (int j = 0; j < 16; ++j) m4[j & 3] = fmaxf(m4[j & 3], __uint_as_float(sv[c * 16 + j]));
           } else {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) m = fmaxf(m, c * 16 + j < L ? __uint_as_float(sv[c * 16 + j]) : -INFINITY);
+            for (int j = 0; j < 16; ++j) m4[j & 3] = fmaxf(m4[j & 3], c * 16 + j < L ? __uint_as_float(sv[c * 16 + j]) : -INFINITY);
           }
         }
+        const float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
         const float off = m * sl2;
 #pragma unroll
         for (int c = 0; c < kLP / 16; ++c) {
@@ -270,14 +289,14 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_bwd_tc_kernel(const __grid_
           }
         }
       }
-      float sum = 0.f;
+      float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int j = 0; j < kLP; ++j) sum += e[j];
-      const float inv = 1.0f / sum;
+      for (int j = 0; j < kLP; ++j) s4[j & 3] += e[j];
+      const float inv = 1.0f / ((s4[0] + s4[1]) + (s4[2] + s4[3]));
 
       // ---- pass B: delta = sum_j P_j dP_j.  TMEM loads are software-pipelined: chunk c+1 is in flight while chunk c
       //      is consumed (tcgen05.wait::ld right after every load would expose its full latency ten times per tile).
-      float delta = 0.f;
+      float d4[4] = {0.f, 0.f, 0.f, 0.f};
       uint32_t dva[16], dvb[16];
       tc::tmem_ld16(t_dp, dva);
       tc::tmem_ld_wait();
@@ -287,10 +306,10 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_bwd_tc_kernel(const __grid_
         uint32_t(&nxt)[16] = (c & 1) ? dva : dvb;
         tc::tmem_ld16(t_dp + ((c + 1 < kLP / 16) ? (c + 1) * 16 : 0), nxt);   // last iteration prefetches pass C's chunk 0
 #pragma unroll
-        for (int j = 0; j < 16; ++j) delta = fmaf(e[c * 16 + j], __uint_as_float(cur[j]), delta);
+        for (int j = 0; j < 16; ++j) d4[j & 3] = fmaf(e[c * 16 + j], __uint_as_float(cur[j]), d4[j & 3]);
         tc::tmem_ld_wait();
       }
-      delta *= inv;
+      const float delta = ((d4[0] + d4[1]) + (d4[2] + d4[3])) * inv;
 
       // ---- pass C: dS = P o (dP - delta) * scale, P: 16-bit pairs in registers; dS -> TMEM over dP -------------------
       const float ps = inv * scale;
@@ -313,7 +332,9 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_bwd_tc_kernel(const __grid_
       }
 
       // ---- P / dS shared-memory tiles free?  (dK/dV MMAs of the previous tile have read them) -- only the stores wait
+      TRACE(2 + g, t, 2);
       if (t > 0) tc::mbar_wait(smem_u32(&pds_free), (uint32_t)(t - 1) & 1u);
+      TRACE(2 + g, t, 3);
 #pragma unroll
       for (int chunk = 0; chunk < kLP / 8; ++chunk) {          // 8 keys = 16 bytes; MN-major, 128B swizzle
         const uint32_t slab = (uint32_t)(chunk >> 3) * kSlab;
@@ -326,10 +347,13 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_bwd_tc_kernel(const __grid_
       tc::fence_proxy_async_smem();     // P / dS written through the generic proxy -> visible to tcgen05.mma
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(smem_u32(&ds_ready[g]));
+      TRACE(2 + g, t, 4);
 
       // ---- dQ epilogue: TMEM -> 16-bit -> swizzled staging tile -> (warp 10) TMA store -------------------------------
       tc::mbar_wait(smem_u32(&dq_full), (uint32_t)t & 1u);
+      TRACE(2 + g, t, 5);
       if (t > 0) tc::mbar_wait(smem_u32(&stage_free), (uint32_t)(t - 1) & 1u);   // previous store has read the staging tile
+      TRACE(2 + g, t, 6);
       tc::fence_after_sync();
       {
         uint32_t ov[64];
@@ -351,6 +375,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_bwd_tc_kernel(const __grid_
       tc::fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) { tc::mbar_arrive(smem_u32(&dq_free)); tc::mbar_arrive(smem_u32(&dq_staged)); }
+      TRACE(2 + g, t, 7);
 
       // ---- (batch, head) boundary: drain dK / dV (lane = key) and add them to the global fp32 accumulators ----------
       if (flush) {
@@ -422,6 +447,12 @@ int launch_bwd_tc(const BwdParams& p, int ctas, cudaStream_t st) {
 }
 
 }  // namespace
+
+#ifdef PEA_TRACE
+extern "C" int pea_debug_bwd_trace(unsigned long long* host, int n) {
+  return (int)cudaMemcpyFromSymbol(host, g_trace, sizeof(unsigned long long) * n);
+}
+#endif
 
 bool attn2_bwd_tc_eligible(const pea_attn2_desc* a) {
   if (a->d != kD || a->L > kLP) return false;

@@ -199,19 +199,21 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_fwd_tc_kernel(const __grid_
         tc::tmem_ld_wait();
       }
       // columns [0, Lfull) need no masking (Lfull = L rounded down to 16: warp-uniform branches below)
-      float m = -INFINITY;
+      // four independent chains: a single softmax warp per scheduler cannot hide a serial 80-long dependency chain
+      float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
       for (int c = 0; c < kLP / 16; ++c) {
         if ((c + 1) * 16 <= L) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) m = fmaxf(m, __uint_as_float(sv[c * 16 + j]));
+          for (int j = 0; j < 16; ++j) m4[j & 3] = fmaxf(m4[j & 3], __uint_as_float(sv[c * 16 + j]));
         } else {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) m = fmaxf(m, c * 16 + j < L ? __uint_as_float(sv[c * 16 + j]) : -INFINITY);
+          for (int j = 0; j < 16; ++j) m4[j & 3] = fmaxf(m4[j & 3], c * 16 + j < L ? __uint_as_float(sv[c * 16 + j]) : -INFINITY);
         }
       }
+      const float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
       const float off = m * sl2;
-      float sum = 0.f;
+      float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int c = 0; c < kLP / 16; ++c) {
         uint32_t pk[8];
@@ -220,7 +222,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_fwd_tc_kernel(const __grid_
           for (int j = 0; j < 8; ++j) {
             const float e0 = ex2(fmaf(__uint_as_float(sv[c * 16 + 2 * j]), sl2, -off));
             const float e1 = ex2(fmaf(__uint_as_float(sv[c * 16 + 2 * j + 1]), sl2, -off));
-            sum += e0 + e1;
+            s4[j & 3] += e0 + e1;
             pk[j] = pack2<T>(e0, e1);
           }
         } else {
@@ -229,7 +231,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_fwd_tc_kernel(const __grid_
             const int j0 = c * 16 + 2 * j;
             const float e0 = j0 < L ? ex2(fmaf(__uint_as_float(sv[j0]), sl2, -off)) : 0.f;
             const float e1 = j0 + 1 < L ? ex2(fmaf(__uint_as_float(sv[j0 + 1]), sl2, -off)) : 0.f;
-            sum += e0 + e1;
+            s4[j & 3] += e0 + e1;
             pk[j] = pack2<T>(e0, e1);
           }
         }
@@ -239,7 +241,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_fwd_tc_kernel(const __grid_
       tc::fence_before_sync();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(smem_u32(&p_ready[g]));
-      const float inv = 1.0f / sum;
+      const float inv = 1.0f / ((s4[0] + s4[1]) + (s4[2] + s4[3]));
 
       // staging tile free again? (this group's previous TMA store must have finished READING it)
       if (t >= 2) {

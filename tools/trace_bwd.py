@@ -1,0 +1,39 @@
+#!/usr/bin/env python
+"""Per-tile event timeline of attn2_bwd_tc_kernel (CTA 0) from an instrumented build (-DPEA_TRACE):
+    PEA_B200_LIB=build/libpea_trace.so python tools/trace_bwd.py [N] [C]
+"""
+import ctypes as C
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+from pea_diffusion_b200 import _lib, ops
+
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
+Cc = int(sys.argv[2]) if len(sys.argv) > 2 else 1280
+H, B, L = Cc // 64, 8, 77
+q = torch.randn(B, N, Cc, device="cuda", dtype=torch.bfloat16)
+kv = torch.randn(B, L, 2 * Cc, device="cuda", dtype=torch.bfloat16)
+do = torch.randn(B, N, Cc, device="cuda", dtype=torch.bfloat16)
+for _ in range(3):
+    ops.attn2_bwd(q, kv, do, H, 0.125)
+torch.cuda.synchronize()
+n = 16 * 64 * 16
+buf = (C.c_ulonglong * n)()
+dll = C.CDLL(_lib.LIB_PATH)
+assert dll.pea_debug_bwd_trace(buf, n) == 0
+ev = lambda role, t, e: buf[(role * 64 + t) * 16 + e]
+t0 = ev(1, 0, 0)
+names = {0: ["ring_empty"], 1: ["sdp:enter", "sdp:ring_full", "main:enter", "ds_ready", "dq_free"],
+         2: ["enter", "sdp_full", "pre_pds", "pds_free", "ds_arrive", "dq_full", "stage_free", "epi_done"]}
+print("cycles relative to the MMA warp's first event; tiles 8..19")
+for t in range(8, 20):
+    g = t & 1
+    row = [f"t{t:2d} g{g}"]
+    row.append("prod " + " ".join(f"{ev(0, t, i) - t0:7d}" for i in range(1)))
+    row.append("| mma " + " ".join(f"{names[1][i]}={ev(1, t, i) - t0:7d}" for i in range(5)))
+    row.append("| sm " + " ".join(f"{names[2][i]}={ev(2 + g, t, i) - t0:7d}" for i in range(8)))
+    print(" ".join(row))
+print("per-tile period (MMA ds_ready to ds_ready):", [ev(1, t + 1, 3) - ev(1, t, 3) for t in range(8, 19)])
