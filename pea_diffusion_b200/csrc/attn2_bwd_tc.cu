@@ -86,6 +86,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_bwd_tc_kernel(const __grid_
   const int item0 = blockIdx.x * p.tiles_per_cta;
   const int ntiles = min(p.tiles_per_cta, p.total_tiles - item0);
   const int tpb = p.tiles_per_bh;
+  if (warp == 0) TRACE(0, 63, 15);   // kernel entry
 
   if (warp == 0 && lane == 0) {
     tc::prefetch_tmap(&p.tmQ); tc::prefetch_tmap(&p.tmdO); tc::prefetch_tmap(&p.tmKV); tc::prefetch_tmap(&p.tmdQ);
@@ -168,12 +169,13 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_bwd_tc_kernel(const __grid_
         const uint32_t qa = (smem + kOffRing + rs * 2 * kTile) >> 4, doa = qa + (kTile >> 4);
         const uint32_t ka = (smem + kOffKV + kb * 2 * kKV) >> 4, va = ka + (kKV >> 4);
         const uint32_t ts = tmem + g * kTPair + kTS, tdp = tmem + g * kTPair + kTdP;
+        // The K steps of one accumulator form a dependent chain that the tensor pipe runs at ~105 clk per step for these
+        // small N (latency, not math: 40-50 clk); two independent accumulators interleaved overlap their latencies.
 #pragma unroll
-        for (int k = 0; k < kD / 16; ++k)
+        for (int k = 0; k < kD / 16; ++k) {
           tc::mma_f16_ss(ts, kDescK | (uint64_t)(qa + k * 2), kDescK | (uint64_t)(ka + k * 2), p.idesc_s, k > 0);
-#pragma unroll
-        for (int k = 0; k < kD / 16; ++k)
           tc::mma_f16_ss(tdp, kDescK | (uint64_t)(doa + k * 2), kDescK | (uint64_t)(va + k * 2), p.idesc_s, k > 0);
+        }
         tc::mma_commit(smem_u32(&sdp_full[g]));
       }
       __syncwarp();
@@ -204,15 +206,14 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_bwd_tc_kernel(const __grid_
         for (int k = 0; k < kLP / 16; ++k)
           tc::mma_f16_ts(tmem + kTdQ, tds + k * 8, kDescMN | (uint64_t)(ka + k * 128), p.idesc_dq, k > 0);
         tc::mma_commit(smem_u32(&dq_full));
-        // dV += P^T dO ; dK += dS^T Q   (reduction over the 128 query rows)
+        // dV += P^T dO ; dK += dS^T Q   (reduction over the 128 query rows; the two chains interleaved)
 #pragma unroll
-        for (int k = 0; k < kQT / 16; ++k)
+        for (int k = 0; k < kQT / 16; ++k) {
           tc::mma_f16_ss(tmem + kTdV, kDescMN | (uint64_t)(pa + k * 128), kDescMN | (uint64_t)(doa + k * 128), p.idesc_dkv,
                          (k > 0) ? 1u : (uint32_t)!first_of_bh);
-#pragma unroll
-        for (int k = 0; k < kQT / 16; ++k)
           tc::mma_f16_ss(tmem + kTdK, kDescMN | (uint64_t)(dsa + k * 128), kDescMN | (uint64_t)(qa + k * 128), p.idesc_dkv,
                          (k > 0) ? 1u : (uint32_t)!first_of_bh);
+        }
         tc::mma_commit(smem_u32(&pds_free));            // P / dS shared-memory tiles reusable
         tc::mma_commit(smem_u32(&ring_empty[rs]));      // Q / dO slot reusable
         if (last_of_bh || last_tile) tc::mma_commit(smem_u32(&dkv_full));
@@ -426,8 +427,10 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_bwd_tc_kernel(const __grid_
     }
   }
 
+  if (warp >= 2 && warp < 10) TRACE(2 + ((warp - 2) >> 2), 63, 14);   // group done (incl. dK/dV flush)
   tc::fence_before_sync();
   __syncthreads();
+  if (warp == 0) TRACE(0, 63, 14);   // all roles done
   if (warp == 1) {
     tc::fence_after_sync();
     tc::tmem_dealloc(tmem, kTmemCols);

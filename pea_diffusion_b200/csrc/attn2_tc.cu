@@ -7,17 +7,19 @@
 //
 // Persistent grid: one CTA per SM, each walking a CONTIGUOUS range of (batch, head, 128-row query tile) work items
 // (query tile fastest), so the Q ring never drains and K|V is reloaded only when (batch, head) changes (double
-// buffered, prefetched).  320 threads:
+// buffered, prefetched).  448 threads:
 //   warp 0      TMA producer: K|V tiles (rows >= L zero-filled by TMA), Q tiles into a 4-deep ring
 //   warp 1      TMEM allocator + MMA issuer, software pipelined  S(t+1) = Q K^T  ahead of  O(t) = P V:
 //                 S = Q K^T   tcgen05.mma SS, M128 N80 K64  -> TMEM S[t&1]
-//                 O = P V     tcgen05.mma TS, M128 N64 K80  -> TMEM O[t&1]   (A = P straight from TMEM)
-//   warps 2..5  softmax/epilogue group 0 (even tiles), warps 6..9 group 1 (odd tiles); thread = query row = TMEM lane:
+//                 O = P [V|1] tcgen05.mma TS, M128 N80 K80  -> TMEM O[t&1]   (A = P straight from TMEM; the ones block
+//                                                                          of B makes column 64 the row sum of P)
+//   warps 2..13 three softmax/epilogue groups of four warps, tiles dealt round-robin; thread = query row = TMEM lane:
 //               tcgen05.ld S, single-pass softmax (all keys are in the tile: no online rescaling and no cross-thread
 //               reduction), unnormalised P -> 16-bit -> tcgen05.st over S's own columns, later tcgen05.ld O, scale by
 //               1/rowsum, 128B-swizzled staging tile, TMA store (clips the N tail).
-// While group 0 runs the softmax of tile t the tensor core already computes S(t+1) for group 1, and the TMA engine is
-// up to four Q tiles ahead.  TMEM: 512 columns (S/P x2, O x2).
+// Per tile a group is mostly waiting on round trips (TMEM ld/st, MMA commits: ~3500 clk of latency for ~1000 clk of issue;
+// profiles/r1_attn2_fwd_timeline.txt), so three groups are in flight; S runs two tiles ahead of P V and the TMA engine up
+// to four Q tiles ahead.  TMEM: 480 of 512 columns (S/P x3, O x3).
 // Algorithmic bytes per tile: 128 x 64 x 2 B in + the same out; FLOPs 4 x 128 x 80 x 64.
 #include "tc05.cuh"
 
@@ -28,15 +30,18 @@ constexpr int kQT = 128;                 // query rows per tile
 constexpr int kD = 64;                   // head dim
 constexpr int kLP = 80;                  // padded key count
 constexpr int kQStages = 4;
-constexpr int kThreads = 320;
+constexpr int kGroups = 3;                    // softmax / epilogue groups (4 warps each), tiles dealt round-robin
+constexpr int kThreads = 64 + kGroups * 128;
 constexpr uint32_t kTmemCols = 512;
-constexpr uint32_t kTmemS = 0, kTmemSStride = 128, kTmemO = 256, kTmemOStride = 64;
+constexpr uint32_t kTmemS = 0, kTmemSStride = 80, kTmemO = 256, kTmemOStride = 80;   // 3 x 80 + 3 x 80 columns <= 512
+constexpr int kNO = kD + 16;                 // O accumulator width: 64 value columns + the row-sum column (16: N granularity)
 constexpr uint32_t kQBytes = kQT * kD * 2;      // 16 KiB
 constexpr uint32_t kKVBytes = kLP * kD * 2;     // 10 KiB each (K, V)
-constexpr uint32_t kOffKV = 0;                                 // 2 buffers x (K 10 KiB | V 10 KiB)
-constexpr uint32_t kOffQ = 2 * 2 * kKVBytes;                   // 4-deep ring
+constexpr uint32_t kKVBuf = 3 * kKVBytes;                      // K | V | ones (the row-sum column block of the B operand)
+constexpr uint32_t kOffKV = 0;                                 // 2 buffers
+constexpr uint32_t kOffQ = 2 * kKVBuf;                         // 4-deep ring
 constexpr uint32_t kOffO = kOffQ + kQStages * kQBytes;         // one staging tile per softmax group
-constexpr uint32_t kSmemBytes = kOffO + 2 * kQBytes + 1024;    // + alignment slack
+constexpr uint32_t kSmemBytes = kOffO + kGroups * kQBytes + 1024;   // one staging tile per softmax group + alignment slack
 
 struct FwdParams {
   CUtensorMap tmQ, tmKV, tmO;
@@ -51,22 +56,52 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8])
                "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
                : "memory");
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
+}
 __device__ __forceinline__ float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// exp2 of two values at once on the MUFU's packed 16-bit path: the result is exactly the 16-bit P pair the tensor core
+// consumes (P is rounded to 16 bits anyway), at half the MUFU issue slots of two fp32 ex2 + a convert.
+template <typename T> __device__ __forceinline__ uint32_t ex2_pair(float x0, float x1);
+template <> __device__ __forceinline__ uint32_t ex2_pair<__nv_bfloat16>(float x0, float x1) {
+  uint32_t r;
+  const uint32_t x = pack2<__nv_bfloat16>(x0, x1);
+  asm("ex2.approx.ftz.bf16x2 %0, %1;" : "=r"(r) : "r"(x));
+  return r;
+}
+template <> __device__ __forceinline__ uint32_t ex2_pair<__half>(float x0, float x1) {
+  uint32_t r;
+  const uint32_t x = pack2<__half>(x0, x1);
+  asm("ex2.approx.f16x2 %0, %1;" : "=r"(r) : "r"(x));
+  return r;
+}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+// Optional per-tile event timeline of CTA 0 (build with -DPEA_TRACE, read with tools/trace_fwd.py).  No-op otherwise.
+#ifdef PEA_TRACE
+__device__ unsigned long long g_trace_fwd[16 * 64 * 16];   // [role][tile][event]
+#define TRACE(role, tile, ev) do { if (blockIdx.x == 0 && (tile) < 64 && lane == 0) g_trace_fwd[((role) * 64 + (tile)) * 16 + (ev)] = clock64(); } while (0)
+#else
+#define TRACE(role, tile, ev) do { } while (0)
+#endif
 
 template <typename T>
 __global__ void __launch_bounds__(kThreads, 1) attn2_fwd_tc_kernel(const __grid_constant__ FwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t kv_full[2], kv_empty[2], q_full[kQStages], q_empty[kQStages];
-  __shared__ __align__(8) uint64_t s_full[2], p_ready[2], o_full[2], tmem_free[2];
+  __shared__ __align__(8) uint64_t s_full[kGroups], p_ready[kGroups], o_full[kGroups], tmem_free[kGroups];
   __shared__ uint32_t tmem_slot;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  if (warp == 0) TRACE(0, 0, 15);   // kernel entry
 
   // ---- this CTA's contiguous range of work items; item = bh * tiles_per_bh + tile ----------------------------------
   const int item0 = blockIdx.x * p.tiles_per_cta;
@@ -76,8 +111,9 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_fwd_tc_kernel(const __grid_
   if (warp == 0 && lane == 0) {
     tc::prefetch_tmap(&p.tmQ); tc::prefetch_tmap(&p.tmKV); tc::prefetch_tmap(&p.tmO);
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      tc::mbar_init(smem_u32(&kv_full[i]), 1); tc::mbar_init(smem_u32(&kv_empty[i]), 1);
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(smem_u32(&kv_full[i]), 1); tc::mbar_init(smem_u32(&kv_empty[i]), 1); }
+#pragma unroll
+    for (int i = 0; i < kGroups; ++i) {
       tc::mbar_init(smem_u32(&s_full[i]), 1); tc::mbar_init(smem_u32(&p_ready[i]), 4);
       tc::mbar_init(smem_u32(&o_full[i]), 1); tc::mbar_init(smem_u32(&tmem_free[i]), 4);
     }
@@ -86,10 +122,21 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_fwd_tc_kernel(const __grid_
     tc::fence_mbar_init();
   }
   if (warp == 1) tc::tmem_alloc(smem_u32(&tmem_slot), kTmemCols);
+  if (warp >= 2) {
+    // B operand of O = P V is [V | 1]: columns 64..79 of the accumulator then hold the row sum of the ROUNDED P the tensor
+    // core actually multiplies, so the softmax threads never add it up.  All-ones is swizzle invariant: plain fill.
+    const uint32_t one2 = pack2<T>(1.0f, 1.0f);
+    for (uint32_t i = threadIdx.x - 64; i < 2 * kKVBytes / 16; i += kThreads - 64) {
+      const uint32_t a = smem + kOffKV + (i / (kKVBytes / 16)) * kKVBuf + 2 * kKVBytes + (i % (kKVBytes / 16)) * 16;
+      asm volatile("st.shared.v4.u32 [%0], {%1,%1,%1,%1};" ::"r"(a), "r"(one2) : "memory");
+    }
+    tc::fence_proxy_async_smem();
+  }
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem = tmem_slot;
+  if (warp == 0) TRACE(0, 0, 14);   // prologue done (barriers, TMEM)
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -104,8 +151,8 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_fwd_tc_kernel(const __grid_
         if (tc::elect_one()) {
           const uint32_t bk = smem_u32(&kv_full[kb]);
           tc::mbar_expect_tx(bk, 2 * kKVBytes);
-          tc::tma_load_3d(smem + kOffKV + kb * 2 * kKVBytes, &p.tmKV, bk, h * kD, 0, b);
-          tc::tma_load_3d(smem + kOffKV + kb * 2 * kKVBytes + kKVBytes, &p.tmKV, bk, p.C + h * kD, 0, b);
+          tc::tma_load_3d(smem + kOffKV + kb * kKVBuf, &p.tmKV, bk, h * kD, 0, b);
+          tc::tma_load_3d(smem + kOffKV + kb * kKVBuf + kKVBytes, &p.tmKV, bk, p.C + h * kD, 0, b);
         }
         __syncwarp();
         cur_bh = bh;
@@ -113,6 +160,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_fwd_tc_kernel(const __grid_
       }
       const int s = t % kQStages;
       tc::mbar_wait(smem_u32(&q_empty[s]), ((uint32_t)(t / kQStages) & 1u) ^ 1u);
+      TRACE(0, t, 0);
       if (tc::elect_one()) {
         const uint32_t fb = smem_u32(&q_full[s]);
         tc::mbar_expect_tx(fb, kQBytes);
@@ -125,7 +173,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_fwd_tc_kernel(const __grid_
     // K-major tiles (Q, K): 128-byte rows, 8-row groups 1024 B apart; K=16 step = 32 B inside the swizzle atom.
     // MN-major tile (V as B of P V): [key][d], 16 keys per K step = 2048 B.
     constexpr uint64_t kDescK = ((uint64_t)1 << 16) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
-    constexpr uint64_t kDescMN = ((uint64_t)(8192u >> 4) << 16) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
+    constexpr uint64_t kDescMN = ((uint64_t)(kKVBytes >> 4) << 16) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
     int s_bh = -1, s_kvn = 0;       // K|V bookkeeping of the S stream (runs one tile ahead of the P V stream)
     int o_bh = -1, o_kvn = 0;
     auto issue_s = [&](int t) {
@@ -135,12 +183,15 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_fwd_tc_kernel(const __grid_
         s_bh = bh;
         ++s_kvn;
       }
-      const int kb = (s_kvn - 1) & 1, qs = t % kQStages, j = t & 1;
+      const int kb = (s_kvn - 1) & 1, qs = t % kQStages, j = t % kGroups;
+      TRACE(1, t, 0);
       tc::mbar_wait(smem_u32(&q_full[qs]), (uint32_t)(t / kQStages) & 1u);
-      if (t >= 2) tc::mbar_wait(smem_u32(&tmem_free[j]), (uint32_t)((t >> 1) - 1) & 1u);  // S/P/O[j] of tile t-2 drained
+      TRACE(1, t, 1);
+      // S/P[j] of tile t-2 need no barrier: P(t-2) was consumed by the P V MMA issued earlier by this same thread, and
+      // tcgen05.mma executes in issue order.  Only O[j] is guarded (below, before P V(t)).
       tc::fence_after_sync();
       if (tc::elect_one()) {
-        const uint32_t qa = (smem + kOffQ + qs * kQBytes) >> 4, ka = (smem + kOffKV + kb * 2 * kKVBytes) >> 4;
+        const uint32_t qa = (smem + kOffQ + qs * kQBytes) >> 4, ka = (smem + kOffKV + kb * kKVBuf) >> 4;
 #pragma unroll
         for (int k = 0; k < kD / 16; ++k)
           tc::mma_f16_ss(tmem + kTmemS + j * kTmemSStride, kDescK | (uint64_t)(qa + k * 2), kDescK | (uint64_t)(ka + k * 2), p.idesc_s, k > 0);
@@ -149,17 +200,23 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_fwd_tc_kernel(const __grid_
       }
       __syncwarp();
     };
+    // S runs two tiles ahead of P V: S(t+2) reuses the S/P buffer of tile t-1, whose P V was issued one iteration ago
+    // (tcgen05.mma executes in issue order), so the softmax groups never wait for S.
     if (ntiles > 0) issue_s(0);
+    if (ntiles > 1) issue_s(1);
     for (int t = 0; t < ntiles; ++t) {
-      if (t + 1 < ntiles) issue_s(t + 1);
-      const int bh = (item0 + t) / tpb, j = t & 1;
+      if (t + 2 < ntiles) issue_s(t + 2);
+      const int bh = (item0 + t) / tpb, j = t % kGroups;
       if (bh != o_bh) { o_bh = bh; ++o_kvn; }
       const int kb = (o_kvn - 1) & 1;
       const bool last_of_bh = (t + 1 < ntiles) && ((item0 + t + 1) / tpb != bh);
-      tc::mbar_wait(smem_u32(&p_ready[j]), (uint32_t)(t >> 1) & 1u);
+      TRACE(1, t, 2);
+      tc::mbar_wait(smem_u32(&p_ready[j]), (uint32_t)(t / kGroups) & 1u);
+      TRACE(1, t, 3);
+      if (t >= kGroups) tc::mbar_wait(smem_u32(&tmem_free[j]), (uint32_t)(t / kGroups - 1) & 1u);  // O[j] of tile t-3 read out
       tc::fence_after_sync();
       if (tc::elect_one()) {
-        const uint32_t va = (smem + kOffKV + kb * 2 * kKVBytes + kKVBytes) >> 4;
+        const uint32_t va = (smem + kOffKV + kb * kKVBuf + kKVBytes) >> 4;
         const uint32_t tp = tmem + kTmemS + j * kTmemSStride, to = tmem + kTmemO + j * kTmemOStride;
 #pragma unroll
         for (int k = 0; k < kLP / 16; ++k)  // A = P from TMEM (8 packed columns per K=16 step), B = V
@@ -171,21 +228,22 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_fwd_tc_kernel(const __grid_
     }
   } else {
     // ===== softmax + epilogue groups: warp w owns TMEM lanes [32*(w%4), +32); thread = query row =====
-    const int g = (warp - 2) >> 2;                       // group 0: warps 2..5 (even tiles), group 1: warps 6..9 (odd tiles)
+    const int g = (warp - 2) >> 2;                       // group g: warps 2+4g .. 5+4g, tiles g, g+3, g+6, ...
     const int q = warp & 3;
     const int row = q * 32 + lane;                       // row inside the tile
     const uint32_t t_s = tmem + kTmemS + g * kTmemSStride + ((uint32_t)(q * 32) << 16);
     const uint32_t t_o = tmem + kTmemO + g * kTmemOStride + ((uint32_t)(q * 32) << 16);
-    const uint32_t o_stage = smem + kOffO + g * kQBytes;
     const bool issuer = threadIdx.x == 64 + g * 128;
     const int L = p.L;
     const float sl2 = p.scale_log2;
-    for (int t = g; t < ntiles; t += 2) {
-      const uint32_t ph = (uint32_t)(t >> 1) & 1u;
+    for (int t = g; t < ntiles; t += kGroups) {
+      const uint32_t ph = (uint32_t)(t / kGroups) & 1u;
       const int item = item0 + t;
       const int bh = item / tpb, tile = item - bh * tpb;
       const int b = bh / p.H, h = bh - b * p.H;
+      TRACE(2 + g, t, 0);
       tc::mbar_wait(smem_u32(&s_full[g]), ph);
+      TRACE(2 + g, t, 1);
       tc::fence_after_sync();
       uint32_t sv[kLP];
       {
@@ -213,26 +271,19 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_fwd_tc_kernel(const __grid_
       }
       const float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
       const float off = m * sl2;
-      float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int c = 0; c < kLP / 16; ++c) {
         uint32_t pk[8];
         if ((c + 1) * 16 <= L) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float e0 = ex2(fmaf(__uint_as_float(sv[c * 16 + 2 * j]), sl2, -off));
-            const float e1 = ex2(fmaf(__uint_as_float(sv[c * 16 + 2 * j + 1]), sl2, -off));
-            s4[j & 3] += e0 + e1;
-            pk[j] = pack2<T>(e0, e1);
-          }
+          for (int j = 0; j < 8; ++j)
+            pk[j] = ex2_pair<T>(fmaf(__uint_as_float(sv[c * 16 + 2 * j]), sl2, -off), fmaf(__uint_as_float(sv[c * 16 + 2 * j + 1]), sl2, -off));
         } else {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const int j0 = c * 16 + 2 * j;
-            const float e0 = j0 < L ? ex2(fmaf(__uint_as_float(sv[j0]), sl2, -off)) : 0.f;
-            const float e1 = j0 + 1 < L ? ex2(fmaf(__uint_as_float(sv[j0 + 1]), sl2, -off)) : 0.f;
-            s4[j & 3] += e0 + e1;
-            pk[j] = pack2<T>(e0, e1);
+            const int j0 = c * 16 + 2 * j;   // masked keys: exp2(-inf) = 0
+            pk[j] = ex2_pair<T>(j0 < L ? fmaf(__uint_as_float(sv[j0]), sl2, -off) : -INFINITY,
+                                j0 + 1 < L ? fmaf(__uint_as_float(sv[j0 + 1]), sl2, -off) : -INFINITY);
           }
         }
         tmem_st8(t_s + c * 8, pk);   // P (16-bit pairs) over S's own columns: this thread's row only
@@ -241,22 +292,28 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_fwd_tc_kernel(const __grid_
       tc::fence_before_sync();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(smem_u32(&p_ready[g]));
-      const float inv = 1.0f / ((s4[0] + s4[1]) + (s4[2] + s4[3]));
+      TRACE(2 + g, t, 2);
 
       // staging tile free again? (this group's previous TMA store must have finished READING it)
-      if (t >= 2) {
+      const uint32_t o_stage = smem + kOffO + (uint32_t)g * kQBytes;
+      if (t >= kGroups) {
         if (issuer) tc::tma_store_wait_read<0>();
         named_bar_sync(1 + g, 128);
       }
+      TRACE(2 + g, t, 3);
       tc::mbar_wait(smem_u32(&o_full[g]), ph);
+      TRACE(2 + g, t, 4);
       tc::fence_after_sync();
       {
         uint32_t ov[64];
         uint32_t(&o0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&ov[0]);
         uint32_t(&o1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&ov[32]);
+        uint32_t rs[8];                       // column 64 = sum_j P_j (columns 65..79 repeat it)
         tc::tmem_ld32(t_o, o0);
         tc::tmem_ld32(t_o + 32, o1);
+        tmem_ld8(t_o + 64, rs);
         tc::tmem_ld_wait();
+        const float inv = 1.0f / __uint_as_float(rs[0]);
 #pragma unroll
         for (int chunk = 0; chunk < 8; ++chunk) {   // 16-byte chunk of the 128-byte row; TMA SWIZZLE_128B: chunk ^= row % 8
           uint4 u;
@@ -277,8 +334,10 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_fwd_tc_kernel(const __grid_
         tc::tma_store_3d(&p.tmO, o_stage, h * kD, tile * kQT, b);
         tc::tma_store_commit();
       }
+      TRACE(2 + g, t, 5);
     }
     if (issuer) tc::tma_store_wait<0>();
+    TRACE(2 + g, 63, 6);   // group done (stores complete for the issuer's lane 0)
   }
 
   tc::fence_before_sync();
@@ -302,6 +361,12 @@ int launch_fwd_tc(const FwdParams& p, int units, cudaStream_t st) {
 }
 
 }  // namespace
+
+#ifdef PEA_TRACE
+extern "C" int pea_debug_fwd_trace(unsigned long long* host, int n) {
+  return (int)cudaMemcpyFromSymbol(host, g_trace_fwd, sizeof(unsigned long long) * n);
+}
+#endif
 
 // Called by pea_attn2_fwd (attn2_mma.cu) when head_dim == 64 and the layout fits TMA (16-byte strides).
 int attn2_fwd_tc(const pea_attn2_desc* a, cudaStream_t st) {
@@ -337,7 +402,7 @@ int attn2_fwd_tc(const pea_attn2_desc* a, cudaStream_t st) {
   p.tiles_per_cta = (p.total_tiles + slots - 1) / slots;
   const int units = (p.total_tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
   p.idesc_s = tc::make_idesc(fp16 ? 0 : 1, 128, kLP, 0, 0);
-  p.idesc_o = tc::make_idesc(fp16 ? 0 : 1, 128, kD, 0, 1);
+  p.idesc_o = tc::make_idesc(fp16 ? 0 : 1, 128, kNO, 0, 1);
   return fp16 ? launch_fwd_tc<__half>(p, units, st) : launch_fwd_tc<__nv_bfloat16>(p, units, st);
 }
 

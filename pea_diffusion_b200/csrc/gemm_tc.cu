@@ -19,6 +19,10 @@
 // fp32-accurate mode: operands are sums of up to 3 bf16 planes; per K step the kernel issues the cross products
 // A[i] B[j], i + j < S.  All planes of a stage share one mbarrier transaction.
 #include <stdlib.h>
+#include <string.h>
+
+#include <mutex>
+#include <unordered_map>
 
 #include "tc05.cuh"
 
@@ -400,9 +404,36 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+namespace {
+struct TmapKey {
+  const void* base; int rank; int fp16; uint64_t dims[3]; uint64_t strides[2]; uint32_t box[3];
+  bool operator==(const TmapKey& o) const { return memcmp(this, &o, sizeof(TmapKey)) == 0; }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    const uint64_t* w = reinterpret_cast<const uint64_t*>(&k);
+    uint64_t h = 1469598103934665603ull;
+    for (size_t i = 0; i < sizeof(TmapKey) / 8; ++i) h = (h ^ w[i]) * 1099511628211ull;
+    return (size_t)h;
+  }
+};
+}  // namespace
+
+// Descriptors are pure functions of (pointer, shape, strides, box): a training step re-launches the same ~250 kernels on
+// the same buffers every iteration, so encodes (1-2 us of driver time each, 3-4 per launch) are cached process-wide.
 int encode_tmap_16bit(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                       const uint32_t* box, bool fp16) {
   static EncodeTiledFn fn = nullptr;
+  static std::mutex mu;
+  static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
+  TmapKey key;
+  memset(&key, 0, sizeof(key));
+  key.base = base; key.rank = rank; key.fp16 = fp16 ? 1 : 0;
+  for (int i = 0; i < rank; ++i) { key.dims[i] = dims[i]; key.box[i] = box[i]; }
+  for (int i = 0; i + 1 < rank; ++i) key.strides[i] = strides_bytes[i];
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find(key);
+  if (it != cache.end()) { *out = it->second; return PEA_OK; }
   if (!fn) {
     void* sym = nullptr;
     cudaDriverEntryPointQueryResult qres;
@@ -427,6 +458,8 @@ int encode_tmap_16bit(CUtensorMap* out, const void* base, int rank, const uint64
               (unsigned long long)(rank > 1 ? strides_bytes[0] : 0), box[0], rank > 1 ? box[1] : 1);
     return PEA_ECUDA;
   }
+  if (cache.size() >= 8192) cache.clear();
+  cache.emplace(key, *out);
   return PEA_OK;
 }
 

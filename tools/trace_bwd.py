@@ -25,15 +25,18 @@ buf = (C.c_ulonglong * n)()
 dll = C.CDLL(_lib.LIB_PATH)
 assert dll.pea_debug_bwd_trace(buf, n) == 0
 ev = lambda role, t, e: buf[(role * 64 + t) * 16 + e]
-t0 = ev(1, 0, 0)
+t0 = ev(0, 63, 15)
+print("kernel entry -> all roles done:", ev(0, 63, 14) - t0, "cycles; groups done at", ev(2, 63, 14) - t0, ev(3, 63, 14) - t0)
 names = {0: ["ring_empty"], 1: ["sdp:enter", "sdp:ring_full", "main:enter", "ds_ready", "dq_free"],
          2: ["enter", "sdp_full", "pre_pds", "pds_free", "ds_arrive", "dq_full", "stage_free", "epi_done"]}
-print("cycles relative to the MMA warp's first event; tiles 8..19")
-for t in range(8, 20):
+ntiles = (B * H * ((N + 127) // 128) + 147) // 148
+lo, hi = (8, 20) if ntiles > 24 else (0, ntiles)
+print(f"cycles relative to kernel entry; tiles {lo}..{hi - 1} of {ntiles}")
+for t in range(lo, hi):
     g = t & 1
     row = [f"t{t:2d} g{g}"]
     row.append("prod " + " ".join(f"{ev(0, t, i) - t0:7d}" for i in range(1)))
     row.append("| mma " + " ".join(f"{names[1][i]}={ev(1, t, i) - t0:7d}" for i in range(5)))
     row.append("| sm " + " ".join(f"{names[2][i]}={ev(2 + g, t, i) - t0:7d}" for i in range(8)))
     print(" ".join(row))
-print("per-tile period (MMA ds_ready to ds_ready):", [ev(1, t + 1, 3) - ev(1, t, 3) for t in range(8, 19)])
+print("per-tile period (MMA ds_ready to ds_ready):", [ev(1, t + 1, 3) - ev(1, t, 3) for t in range(lo, hi - 1)])

@@ -1,0 +1,37 @@
+#!/usr/bin/env python
+"""Per-tile event timeline of attn2_fwd_tc_kernel (CTA 0) from an instrumented build (-DPEA_TRACE):
+    PEA_B200_LIB=build/libpea_trace.so python tools/trace_fwd.py [N] [C]
+"""
+import ctypes as C
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+from pea_diffusion_b200 import _lib, ops
+
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+Cc = int(sys.argv[2]) if len(sys.argv) > 2 else 1280
+H, B, L = Cc // 64, 8, 77
+q = torch.randn(B, N, Cc, device="cuda", dtype=torch.bfloat16)
+kv = torch.randn(B, L, 2 * Cc, device="cuda", dtype=torch.bfloat16)
+scratch = torch.empty(256 << 20, device="cuda", dtype=torch.uint8)
+for _ in range(3):
+    scratch.view(torch.int32).sum()
+    ops.attn2_fwd(q, kv, H, 0.125)
+torch.cuda.synchronize()
+n = 16 * 64 * 16
+buf = (C.c_ulonglong * n)()
+dll = C.CDLL(_lib.LIB_PATH)
+assert dll.pea_debug_fwd_trace(buf, n) == 0
+ev = lambda role, t, e: buf[(role * 64 + t) * 16 + e]
+t0 = ev(0, 0, 15)
+print(f"N={N} C={Cc}: cycles since kernel entry of CTA 0 (cold L2)")
+print("prologue done", ev(0, 0, 14) - t0)
+ntiles = (B * H * ((N + 127) // 128) + 147) // 148
+for t in range(min(ntiles, 12)):
+    g = t & 1
+    print(f"t{t:2d} g{g} prod issue {ev(0, t, 0) - t0:6d} | mma q_wait {ev(1, t, 0) - t0:6d} q_full {ev(1, t, 1) - t0:6d} p_wait {ev(1, t, 2) - t0:6d} p_ready {ev(1, t, 3) - t0:6d}"
+          f" | sm s_wait {ev(2 + g, t, 0) - t0:6d} s_full {ev(2 + g, t, 1) - t0:6d} p_arrive {ev(2 + g, t, 2) - t0:6d} o_wait {ev(2 + g, t, 3) - t0:6d} o_full {ev(2 + g, t, 4) - t0:6d} stored {ev(2 + g, t, 5) - t0:6d}")
+print("group done:", ev(2, 63, 6) - t0, ev(3, 63, 6) - t0)
