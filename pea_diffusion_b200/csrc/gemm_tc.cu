@@ -152,6 +152,68 @@ __device__ __forceinline__ float round16(float v, int dtype) {
   return dtype == PEA_F16 ? __half2float(__float2half_rn(v)) : __bfloat162float(__float2bfloat16_rn(v));
 }
 
+// Epilogue of one 128-row x BN-column accumulator tile for one thread (= one output row): TMEM -> registers -> fused math
+// -> global.  `tacc` = TMEM address of the accumulator's column 0 in this warp's lane quadrant.
+template <int BN>
+__device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tacc, int row, int n0, bool al0, bool al1, bool alx) {
+  const bool row_ok = row < p.M;
+  const float* radd = (p.rowadd && row_ok) ? p.rowadd + (long long)(row / p.rowadd_group) * p.N : nullptr;
+#pragma unroll 1
+  for (int c = 0; c < BN / 32; ++c) {
+    uint32_t v[32];
+    tc::tmem_ld32(tacc + (uint32_t)(c * 32), v);
+    tc::tmem_ld_wait();
+    if (!row_ok) continue;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const int n = n0 + c * 32 + g * 8;
+      if (n >= p.N) break;
+      const int valid = min(8, p.N - n);
+      const bool full = valid == 8;
+      float f[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = p.alpha * __uint_as_float(v[g * 8 + j]);
+      if (p.bias) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (j < valid) f[j] += p.bias[n + j];
+      }
+      if (p.aux) {
+        float a[8];
+        load8(p.aux, p.aux_dtype, (long long)row * p.ldaux + n, full && alx, valid, a);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] *= gelu_exact_grad(a[j]);
+      }
+      if (radd) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (j < valid) f[j] = fmaf(radd[n + j], p.rowadd_scale, f[j]);
+      }
+      if (p.out0) store8(p.out0, p.out0_dtype, (long long)row * p.ldo0 + n, full && al0, valid, f, p.out0_mode);
+      if (p.out1_nsplit > 0) {
+        if (p.act) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] = gelu_exact(f[j]);
+        }
+        for (int s = 0; s < p.out1_nsplit; ++s) {
+          float r[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { r[j] = round16(f[j], p.out1_dtype); f[j] -= r[j]; }
+          store8(p.out1[s], p.out1_dtype, (long long)row * p.ldo1 + n, full && al1, valid, r, 0);
+        }
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void epilogue_alignment(const GemmParams& p, bool& al0, bool& al1, bool& alx) {
+  al0 = p.out0 && (p.ldo0 % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.out0) & (p.out0_dtype == PEA_F32 ? 31 : 15)) == 0);
+  al1 = p.out1_nsplit > 0 && (p.ldo1 % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.out1[0]) & 15) == 0) &&
+        (p.out1_nsplit < 2 || (reinterpret_cast<uintptr_t>(p.out1[1]) & 15) == 0) &&
+        (p.out1_nsplit < 3 || (reinterpret_cast<uintptr_t>(p.out1[2]) & 15) == 0);
+  alx = p.aux && (p.ldaux % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.aux) & (p.aux_dtype == PEA_F32 ? 31 : 15)) == 0);
+}
+
 // SA / SB: operand plane counts; A_MN / B_MN: operand majors.  Everything the issue loops touch is a compile-time
 // constant or a warp-uniform value: the whole producer / MMA warp runs the loop (uniform control flow keeps address
 // and descriptor arithmetic on the uniform datapath) and only the asynchronous instruction itself is issued by one
@@ -284,70 +346,19 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   } else {
     // ===== epilogue: warp w owns TMEM lanes [32*(w%4), +32) = output rows m0 + 32*(w%4) + lane =====
     const int q = warp & 3;
-    const bool al0 = p.out0 && (p.ldo0 % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.out0) & (p.out0_dtype == PEA_F32 ? 31 : 15)) == 0);
-    const bool al1 = p.out1_nsplit > 0 && (p.ldo1 % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.out1[0]) & 15) == 0) &&
-                     (p.out1_nsplit < 2 || (reinterpret_cast<uintptr_t>(p.out1[1]) & 15) == 0) &&
-                     (p.out1_nsplit < 3 || (reinterpret_cast<uintptr_t>(p.out1[2]) & 15) == 0);
-    const bool alx = p.aux && (p.ldaux % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.aux) & (p.aux_dtype == PEA_F32 ? 31 : 15)) == 0);
+    bool al0, al1, alx;
+    epilogue_alignment(p, al0, al1, alx);
     int local = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++local) {
-    int m0, n0, kb_begin, nkb;
-    tile_coords(tile, m0, n0, kb_begin, nkb);
-    const int as = local & 1;
-    const int row = m0 + q * 32 + lane;
-    const bool row_ok = row < p.M;
-    const float* radd = (p.rowadd && row_ok) ? p.rowadd + (long long)(row / p.rowadd_group) * p.N : nullptr;
-    tc::mbar_wait(smem_u32(&acc_full[as]), (uint32_t)(local >> 1) & 1u);
-    tc::fence_after_sync();
-#pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      uint32_t v[32];
-      tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c * 32), v);
-      tc::tmem_ld_wait();
-      if (!row_ok) continue;
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const int n = n0 + c * 32 + g * 8;
-        if (n >= p.N) break;
-        const int valid = min(8, p.N - n);
-        const bool full = valid == 8;
-        float f[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] = p.alpha * __uint_as_float(v[g * 8 + j]);
-        if (p.bias) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            if (j < valid) f[j] += p.bias[n + j];
-        }
-        if (p.aux) {
-          float a[8];
-          load8(p.aux, p.aux_dtype, (long long)row * p.ldaux + n, full && alx, valid, a);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) f[j] *= gelu_exact_grad(a[j]);
-        }
-        if (radd) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            if (j < valid) f[j] = fmaf(radd[n + j], p.rowadd_scale, f[j]);
-        }
-        if (p.out0) store8(p.out0, p.out0_dtype, (long long)row * p.ldo0 + n, full && al0, valid, f, p.out0_mode);
-        if (p.out1_nsplit > 0) {
-          if (p.act) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] = gelu_exact(f[j]);
-          }
-          for (int s = 0; s < p.out1_nsplit; ++s) {
-            float r[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { r[j] = round16(f[j], p.out1_dtype); f[j] -= r[j]; }
-            store8(p.out1[s], p.out1_dtype, (long long)row * p.ldo1 + n, full && al1, valid, r, 0);
-          }
-        }
-      }
-    }
-    tc::fence_before_sync();
-    __syncwarp();
-    if (lane == 0) tc::mbar_arrive(smem_u32(&acc_empty[as]));   // this accumulator may be overwritten (tile local + 2)
+      int m0, n0, kb_begin, nkb;
+      tile_coords(tile, m0, n0, kb_begin, nkb);
+      const int as = local & 1;
+      tc::mbar_wait(smem_u32(&acc_full[as]), (uint32_t)(local >> 1) & 1u);
+      tc::fence_after_sync();
+      epilogue_tile<BN>(p, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN), m0 + q * 32 + lane, n0, al0, al1, alx);
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(smem_u32(&acc_empty[as]));   // this accumulator may be overwritten (tile local + 2)
     }
   }
 
@@ -356,6 +367,145 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   if (warp == 1) {
     tc::fence_after_sync();
     tc::tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2): a cluster of two CTAs on adjacent SMs computes one 256 x 256 tile.  Each CTA stages its
+// own 128 rows of A and its own 128-row half of the B tile; the leader's single thread issues M256 N256 K16 MMAs that read
+// both CTAs' shared memory, so every SM fetches only 8 KB of operands per 128-cycle MMA (64 B/clk -- the measured SS
+// operand-fetch rate) instead of 12 KB: the tensor pipe is no longer operand-starved (67 % -> ~95 % duty).
+// Barrier protocol: TMA loads of BOTH CTAs credit the LEADER's full barrier; tcgen05.commit multicasts to the empty /
+// accumulator-full barriers of both CTAs; the peer's epilogue warps release the accumulator on the leader's barrier through
+// a shared::cluster arrive.  Single-plane operands only (the throughput mode).
+template <int A_MN, int B_MN>
+__global__ void __launch_bounds__(kThreads, 1) gemm_tc2_kernel(const __grid_constant__ GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t acc_full[2], acc_empty[2];
+  __shared__ uint32_t tmem_base_slot;
+
+  constexpr int BN = 256;                                   // per pair; each CTA stages BN / 2 rows of B
+  constexpr uint32_t kBHalf = (uint32_t)(BN / 2) * BK * 2;   // 16 KiB
+  constexpr uint32_t kStageBytes = kTileBytes + kBHalf;      // per CTA
+  constexpr uint32_t kTmemCols = 2 * BN;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = tc::cluster_ctarank();
+  const bool leader = rank == 0;
+  const uint32_t tiles = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int stages = p.stages;
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  auto tile_coords = [&](int tile, int& m0, int& n0) {   // m_tiles counts 256-row pair tiles; m fastest
+    const int mi = tile % p.m_tiles, ni = tile / p.m_tiles;
+    m0 = mi * 256; n0 = ni * BN;
+  };
+
+  if (warp == 0 && lane == 0) {
+    tc::prefetch_tmap(&p.tmA[0]);
+    tc::prefetch_tmap(&p.tmB[0]);
+    for (int s = 0; s < stages; ++s) {
+      tc::mbar_init(smem_u32(&full_bar[s]), 1);
+      tc::mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    tc::mbar_init(smem_u32(&acc_full[0]), 1); tc::mbar_init(smem_u32(&acc_full[1]), 1);
+    tc::mbar_init(smem_u32(&acc_empty[0]), 8); tc::mbar_init(smem_u32(&acc_empty[1]), 8);   // 4 epilogue warps x 2 CTAs
+    tc::fence_mbar_init();
+  }
+  if (warp == 1) tc::tmem_alloc_cg2(smem_u32(&tmem_base_slot), kTmemCols);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::cluster_sync();            // the peer's barriers exist before anything arrives on them
+  tc::fence_after_sync();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs): own A rows, own half of B; bytes credited to the leader's full barrier =====
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tile = pair; tile < p.total_tiles; tile += npairs) {
+      int m0, n0;
+      tile_coords(tile, m0, n0);
+      const int ma = m0 + (int)rank * 128, nb = n0 + (int)rank * (BN / 2);
+      for (int it = 0; it < p.kb_total; ++it) {
+        tc::mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
+        if (tc::elect_one()) {
+          if (leader) tc::mbar_expect_tx(smem_u32(&full_bar[s]), 2 * kStageBytes);
+          const uint32_t fb = tc::mapa(smem_u32(&full_bar[s]), 0);   // the leader's barrier, from either CTA
+          const int k0 = it * BK;
+          const uint32_t dst = tiles + (uint32_t)s * kStageBytes;
+          if (!A_MN) tc::tma_load_2d_cg2(dst, &p.tmA[0], fb, k0, ma);
+          else { tc::tma_load_2d_cg2(dst, &p.tmA[0], fb, ma, k0); tc::tma_load_2d_cg2(dst + 8192, &p.tmA[0], fb, ma + 64, k0); }
+          const uint32_t db = dst + kTileBytes;
+          if (!B_MN) tc::tma_load_2d_cg2(db, &p.tmB[0], fb, k0, nb);
+          else { tc::tma_load_2d_cg2(db, &p.tmB[0], fb, nb, k0); tc::tma_load_2d_cg2(db + 8192, &p.tmB[0], fb, nb + 64, k0); }
+        }
+        __syncwarp();
+        if (++s == stages) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: leader CTA only =====
+    if (leader) {
+      constexpr uint32_t kAStep = A_MN ? 2048u : 32u, kBStep = B_MN ? 2048u : 32u;
+      constexpr uint32_t kALbo = A_MN ? (uint32_t)BK * 128u : 16u, kBLbo = B_MN ? (uint32_t)BK * 128u : 16u;
+      constexpr uint64_t kADescHi = ((uint64_t)(kALbo >> 4) << 16) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
+      constexpr uint64_t kBDescHi = ((uint64_t)(kBLbo >> 4) << 16) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
+      const uint32_t idesc = p.idesc;
+      int s = 0;
+      uint32_t ph = 0;
+      int local = 0;
+      for (int tile = pair; tile < p.total_tiles; tile += npairs, ++local) {
+        const int as = local & 1;
+        const uint32_t tmem_acc = tmem_base + (uint32_t)as * BN;
+        tc::mbar_wait(smem_u32(&acc_empty[as]), ((uint32_t)(local >> 1) & 1u) ^ 1u);   // both CTAs' epilogues drained it
+        tc::fence_after_sync();
+        for (int it = 0; it < p.kb_total; ++it) {
+          tc::mbar_wait(smem_u32(&full_bar[s]), ph);
+          tc::fence_after_sync();
+          if (tc::elect_one()) {
+            const uint32_t a_base = (tiles + (uint32_t)s * kStageBytes) >> 4;
+            const uint32_t b_base = a_base + (kTileBytes >> 4);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {
+              const uint64_t da = kADescHi | (uint64_t)(a_base + (uint32_t)((k * kAStep) >> 4));
+              const uint64_t db = kBDescHi | (uint64_t)(b_base + (uint32_t)((k * kBStep) >> 4));
+              tc::mma_f16_ss_cg2(tmem_acc, da, db, idesc, (k == 0) ? (uint32_t)(it > 0) : 1u);
+            }
+            tc::mma_commit_cg2(smem_u32(&empty_bar[s]));                          // stage reusable in BOTH CTAs
+            if (it == p.kb_total - 1) tc::mma_commit_cg2(smem_u32(&acc_full[as])); // accumulator complete in BOTH CTAs
+          }
+          __syncwarp();
+          if (++s == stages) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else {
+    // ===== epilogue (both CTAs): rows m0 + 128 * rank + 32 * (w % 4) + lane of the pair tile, all BN columns =====
+    const int q = warp & 3;
+    bool al0, al1, alx;
+    epilogue_alignment(p, al0, al1, alx);
+    const uint32_t leader_empty0 = tc::mapa(smem_u32(&acc_empty[0]), 0), leader_empty1 = tc::mapa(smem_u32(&acc_empty[1]), 0);
+    int local = 0;
+    for (int tile = pair; tile < p.total_tiles; tile += npairs, ++local) {
+      int m0, n0;
+      tile_coords(tile, m0, n0);
+      const int as = local & 1;
+      tc::mbar_wait(smem_u32(&acc_full[as]), (uint32_t)(local >> 1) & 1u);
+      tc::fence_after_sync();
+      epilogue_tile<BN>(p, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN), m0 + (int)rank * 128 + q * 32 + lane, n0, al0, al1, alx);
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive_cluster(as ? leader_empty1 : leader_empty0);
+    }
+  }
+
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::cluster_sync();            // nobody exits (or frees TMEM) while the peer may still touch its barriers / TMEM
+  if (warp == 1) {
+    tc::fence_after_sync();
+    tc::tmem_dealloc_cg2(tmem_base, kTmemCols);
   }
 }
 
@@ -378,6 +528,37 @@ int dispatch_major(const GemmParams& p, int ctas, size_t smem, cudaStream_t st) 
     case 1: return launch<SA, SB, 0, 1, BN>(p, ctas, smem, st);
     case 2: return launch<SA, SB, 1, 0, BN>(p, ctas, smem, st);
     default: return launch<SA, SB, 1, 1, BN>(p, ctas, smem, st);
+  }
+}
+
+template <int A_MN, int B_MN>
+int launch_pair(const GemmParams& p, int pairs, size_t smem, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    PEA_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemBudget + 1024)));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  PEA_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc2_kernel<A_MN, B_MN>, p));
+  PEA_LAUNCH_CHECK();
+  return PEA_OK;
+}
+
+int dispatch_pair(const GemmParams& p, int pairs, size_t smem, cudaStream_t st) {
+  switch (p.a_mn * 2 + p.b_mn) {
+    case 0: return launch_pair<0, 0>(p, pairs, smem, st);
+    case 1: return launch_pair<0, 1>(p, pairs, smem, st);
+    case 2: return launch_pair<1, 0>(p, pairs, smem, st);
+    default: return launch_pair<1, 1>(p, pairs, smem, st);
   }
 }
 
@@ -489,6 +670,18 @@ extern "C" int pea_gemm(const pea_gemm_desc* g, void* stream) {
   const int m_tiles = (g->M + BM - 1) / BM;
   int bn = 128;
   if (has_bn256(p.sa, p.sb) && g->split_k <= 1 && (long long)m_tiles * ((g->N + 255) / 256) >= num_sms()) bn = 256;
+  // CTA pairs (256 x 256 per two SMs) when there is a pair tile per SM pair and the row padding to 256 does not eat the
+  // gain (measured: 1 329 vs 1 169 TF/s at 4096^3, x1.14; at M = 616 the 768-row padding loses: 895 vs 1 031 TF/s);
+  // PEA_GEMM_PAIR=0/1 forces the choice for A/B runs.
+  bool pair = false;
+  if (bn == 256) {
+    const long long pm = (g->M + 255) / 256, pn = (g->N + 255) / 256;
+    const double eff_pair = (double)g->M / (256.0 * pm), eff_single = (double)g->M / (128.0 * m_tiles);
+    pair = pm * pn >= num_sms() / 2 && eff_pair * 1.12 > eff_single;
+    static int forced = -2;
+    if (forced == -2) { const char* e = getenv("PEA_GEMM_PAIR"); forced = e ? atoi(e) : -1; }
+    if (forced >= 0) pair = forced != 0;
+  }
   for (int i = 0; i < p.sa; ++i) {
     PEA_CHECK_ARG(g->d_A[i] && (reinterpret_cast<uintptr_t>(g->d_A[i]) & 15) == 0, "gemm: A plane %d null or not 16-byte aligned", i);
     const uint64_t dims[2] = {(uint64_t)(p.a_mn ? g->M : g->K), (uint64_t)(p.a_mn ? g->K : g->M)};
@@ -501,7 +694,7 @@ extern "C" int pea_gemm(const pea_gemm_desc* g, void* stream) {
     PEA_CHECK_ARG(g->d_B[j] && (reinterpret_cast<uintptr_t>(g->d_B[j]) & 15) == 0, "gemm: B plane %d null or not 16-byte aligned", j);
     const uint64_t dims[2] = {(uint64_t)(p.b_mn ? g->N : g->K), (uint64_t)(p.b_mn ? g->K : g->N)};
     const uint64_t str[1] = {(uint64_t)g->ldb * 2};
-    const uint32_t box[2] = {64u, p.b_mn ? 64u : (uint32_t)bn};
+    const uint32_t box[2] = {64u, p.b_mn ? 64u : (pair ? 128u : (uint32_t)bn)};
     int rc = encode_tmap_16bit(&p.tmB[j], g->d_B[j], 2, dims, str, box, fp16);
     if (rc != PEA_OK) return rc;
   }
@@ -514,7 +707,7 @@ extern "C" int pea_gemm(const pea_gemm_desc* g, void* stream) {
   }
   p.kb_per_split = (p.kb_total + splits - 1) / splits;
   splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;  // no empty split
-  p.m_tiles = m_tiles;
+  p.m_tiles = pair ? (g->M + 255) / 256 : m_tiles;
   p.n_tiles = (g->N + bn - 1) / bn;
   p.splits = splits;
   p.total_tiles = p.m_tiles * p.n_tiles * splits;
@@ -522,7 +715,12 @@ extern "C" int pea_gemm(const pea_gemm_desc* g, void* stream) {
   int stages = (int)(kSmemBudget / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   p.stages = stages;
-  p.idesc = tc::make_idesc(fp16 ? 0 : 1, BM, bn, p.a_mn, p.b_mn);
+  p.idesc = tc::make_idesc(fp16 ? 0 : 1, pair ? 256 : BM, bn, p.a_mn, p.b_mn);
+  if (pair) {   // per-CTA stage = A 16 KiB + half of B 16 KiB
+    stages = (int)(kSmemBudget / (2 * kTileBytes));
+    if (stages > kMaxStages) stages = kMaxStages;
+    p.stages = stages;
+  }
   p.alpha = g->alpha;
   p.bias = g->d_bias;
   p.aux = g->d_aux; p.aux_dtype = g->aux_dtype; p.ldaux = g->ldaux;
@@ -536,6 +734,10 @@ extern "C" int pea_gemm(const pea_gemm_desc* g, void* stream) {
   }
   p.out1_nsplit = g->out1_nsplit; p.out1_dtype = g->out1_dtype; p.ldo1 = g->ldo1;
 
+  if (pair) {
+    const int pairs = p.total_tiles < num_sms() / 2 ? p.total_tiles : num_sms() / 2;
+    return dispatch_pair(p, pairs, (size_t)stages * 2 * kTileBytes + 1024, static_cast<cudaStream_t>(stream));
+  }
   const size_t smem = (size_t)stages * stage_bytes + 1024;
   const int ctas = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
   return dispatch(p, bn, ctas, smem, static_cast<cudaStream_t>(stream));

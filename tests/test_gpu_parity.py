@@ -47,6 +47,23 @@ def test_gemm_majors_and_ragged(ops, a_k, b_k, M, N, K):
     assert rel_err(out, ref) < 1e-5  # bf16 products are exact in fp32; only the accumulation order differs
 
 
+@pytest.mark.parametrize("a_k,b_k", [(True, True), (True, False), (False, True), (False, False)])
+@pytest.mark.parametrize("M,N,K", [(2048, 2560, 512), (2000, 2504, 328)])
+def test_gemm_cta_pair_path(ops, a_k, b_k, M, N, K):
+    """Shapes large enough for the cta_group::2 kernel (a 256 x 256 tile per SM pair, M256 MMAs issued by the leader CTA,
+    operands staged by both CTAs), all operand majors, ragged edges."""
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g).to(torch.bfloat16)
+    B = torch.randn(N, K, generator=g).to(torch.bfloat16)
+    ref = A.double() @ B.double().t()
+    a_dev = (A if a_k else A.t().contiguous()).to(DEV)
+    b_dev = (B if b_k else B.t().contiguous()).to(DEV)
+    bias = torch.randn(N, generator=g)
+    out = torch.full((M, N), float("nan"), device=DEV, dtype=torch.float32)
+    ops.gemm([a_dev], [b_dev], M, N, K, a_kmajor=a_k, b_kmajor=b_k, bias=bias.to(DEV), out0=out)
+    assert rel_err(out, ref + bias.double()) < 1e-5
+
+
 @pytest.mark.parametrize("nsplit,tol", [(1, 6e-3), (2, 3e-5), (3, 1.5e-5)])  # 3 planes: limited by the tensor core's fp32 accumulate (truncating alignment), not the split
 def test_gemm_split_precision(ops, nsplit, tol):
     g = torch.Generator().manual_seed(3)
