@@ -76,29 +76,30 @@ class _ProjectAllFn(torch.autograd.Function):
         kv_all = torch.empty(B * L, group.total, device=context.device, dtype=context.dtype)
         ops.gemm([context.reshape(B * L, Dc)], [wcat], B * L, group.total, Dc, out0=kv_all)
         ctx_.group, ctx_.shape, ctx_.dtype = group, (B, L, Dc), context.dtype
-        group.dkv_all = None
-        group.bwd_calls = 0
+        # per-pass state (several passes may be outstanding before their backwards run, e.g. gradient accumulation)
+        state = _PassState()
         if ctx_.needs_input_grad[0]:
-            group.dkv_all = torch.zeros(B, L, group.total, device=context.device, dtype=torch.float32)
+            state.dkv_all = torch.zeros(B, L, group.total, device=context.device, dtype=torch.float32)
+        ctx_.state = group.state = state
         token = context.new_zeros(1)
         ctx_.mark_non_differentiable(kv_all)
         return kv_all, token
 
     @staticmethod
     def backward(ctx_, _g_kv, g_token):
-        group = ctx_.group
+        group, state = ctx_.group, ctx_.state
         B, L, Dc = ctx_.shape
-        if group.bwd_calls != group.fwd_calls_with_grad:
-            raise RuntimeError(f"attn2 group: dContext requested after {group.bwd_calls} of {group.fwd_calls_with_grad} layer "
+        if state.bwd_calls != state.fwd_calls:
+            raise RuntimeError(f"attn2 group: dContext requested after {state.bwd_calls} of {state.fwd_calls} layer "
                                "backwards -- the first attn2 layer is not upstream of all others in this network")
-        wcat = group.weights(ctx_.dtype, group.dkv_all.device)
-        dkv16 = ops.split_planes(group.dkv_all.view(B * L, group.total), 1, ctx_.dtype)
+        wcat = group.weights(ctx_.dtype, state.dkv_all.device)
+        dkv16 = ops.split_planes(state.dkv_all.view(B * L, group.total), 1, ctx_.dtype)
         dctx = torch.zeros(B * L, Dc, device=wcat.device, dtype=torch.float32)
         kb = (group.total + 63) // 64
         tiles = ((B * L + 127) // 128) * ((Dc + 127) // 128)
         split = max(1, min(kb // 8, (4 * group.sms + tiles - 1) // tiles))
         ops.gemm(dkv16, [wcat], B * L, Dc, group.total, b_kmajor=False, out0=dctx, accumulate=True, split_k=split)
-        group.dkv_all = None
+        state.dkv_all = None
         return dctx.view(B, L, Dc).to(ctx_.dtype), None
 
 
@@ -110,23 +111,35 @@ class _Attn2GroupedFn(torch.autograd.Function):
         o = ops.attn2_fwd(q, kv, heads, scale)
         ctx_.save_for_backward(q, kv)
         ctx_.group, ctx_.layer, ctx_.heads, ctx_.scale, ctx_.has_token = group, layer, heads, scale, token is not None
-        ctx_.track = group.dkv_all is not None
+        ctx_.state = group.state
+        ctx_.track = ctx_.state is not None and ctx_.state.dkv_all is not None
         if ctx_.track:
-            group.fwd_calls_with_grad += 1
+            ctx_.state.fwd_calls += 1
         return o
 
     @staticmethod
     def backward(ctx_, do: Tensor):
         q, kv = ctx_.saved_tensors
-        group = ctx_.group
+        group, state = ctx_.group, ctx_.state
         dkv = None
         if ctx_.track:
             off, c2 = group.offsets[ctx_.layer], group.widths[ctx_.layer]
-            dkv = group.dkv_all[:, :, off:off + c2]
+            dkv = state.dkv_all[:, :, off:off + c2]
         dq, _ = ops.attn2_bwd(q, kv, do, ctx_.heads, ctx_.scale, dkv=dkv)
         if ctx_.track:
-            group.bwd_calls += 1
+            state.bwd_calls += 1
         return (dq if ctx_.needs_input_grad[0] else None), (do.new_zeros(1) if ctx_.has_token else None), None, None, None, None, None
+
+
+class _PassState:
+    """What one projection (one UNet pass) shares with its layers' backward: the fp32 dK|dV accumulator of all layers
+    and the forward / backward call counts that guard the single dContext GEMM."""
+    __slots__ = ("dkv_all", "fwd_calls", "bwd_calls")
+
+    def __init__(self):
+        self.dkv_all: Optional[Tensor] = None
+        self.fwd_calls = 0
+        self.bwd_calls = 0
 
 
 class Attn2Group:
@@ -148,9 +161,7 @@ class Attn2Group:
         self._kv_all: Optional[Tensor] = None
         self._token: Optional[Tensor] = None
         self._supported: Optional[bool] = None
-        self.dkv_all: Optional[Tensor] = None
-        self.fwd_calls_with_grad = 0
-        self.bwd_calls = 0
+        self.state: Optional[_PassState] = None
         self.sms = torch.cuda.get_device_properties(0).multi_processor_count if torch.cuda.is_available() else 148
 
     def weights(self, dtype, device) -> Tensor:
@@ -187,7 +198,6 @@ class Attn2Group:
         if not ctx.is_contiguous():
             ctx = ctx.contiguous()
         self._supported = None       # re-validated by the next pass
-        self.fwd_calls_with_grad = 0
         kv_all, token = _ProjectAllFn.apply(ctx, self)
         self._ctx_ref, self._ctx_key = context, key
         self._kv_all = kv_all
@@ -195,7 +205,7 @@ class Attn2Group:
         return kv_all, (token if need_grad else None)
 
     def release(self) -> None:
-        self._ctx_ref = self._kv_all = self._token = self.dkv_all = None
+        self._ctx_ref = self._kv_all = self._token = self.state = None
 
 
 def attn2_core(q: Tensor, context: Tensor, wkv: Tensor, heads: int, scale: Optional[float] = None,

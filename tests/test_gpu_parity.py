@@ -523,9 +523,13 @@ def test_group_projection_matches_per_layer_path():
         procs = attn2.install(unet, group_projection=grouped)
         ctx = torch.randn(2, 77, cfg.cross_attention_dim, device=DEV, dtype=torch.bfloat16,
                           generator=torch.Generator(device=DEV).manual_seed(3)).requires_grad_(True)
+        # two passes outstanding before any backward (gradient accumulation): each keeps its own dK|dV accumulator
+        ctx2 = (ctx.detach() * 0.5 + 0.1).requires_grad_(True)
         out = unet(x, t, ctx, added_cond_kwargs=kw)[0]
-        out.backward(gout)
-        res.append((out.detach().float(), ctx.grad.float()))
+        out2 = unet(x, t, ctx2, added_cond_kwargs=kw)[0]
+        (out * gout.float()).sum().backward()
+        (out2 * gout.float()).sum().backward()
+        res.append((torch.cat([out, out2]).detach().float(), torch.cat([ctx.grad, ctx2.grad]).float()))
         has_group = any(getattr(p, "group", None) is not None for p in procs.values())
         assert has_group == grouped
     assert rel_err(res[1][0], res[0][0]) < 1e-2
