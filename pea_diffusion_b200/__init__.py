@@ -8,5 +8,6 @@ from . import _lib  # noqa: F401  (fails loudly when the CUDA library has not be
 from .adapter import MLP, MLP_Legacy, MLP_SD, MLP_plus  # noqa: F401
 from .attn2 import PEAAttn2Processor, attn2_core, install  # noqa: F401
 from .kd_loss import kd_loss  # noqa: F401
+from .staging import BatchStager  # noqa: F401
 
 __version__ = "0.1.0"

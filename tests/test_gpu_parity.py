@@ -534,3 +534,34 @@ def test_group_projection_matches_per_layer_path():
         assert has_group == grouped
     assert rel_err(res[1][0], res[0][0]) < 1e-2
     assert rel_err(res[1][1], res[0][1]) < 3e-2
+
+
+# ------------------------------------------------------------------------------------------------- input staging (N4)
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("depth", [1, 2, 3])
+def test_batch_stager_prefetch_is_ordered_and_exact(depth):
+    """Double-buffered host -> HBM staging (train_sdxl_zh.py:311-397 consumes a collated CPU dict): every yielded device batch
+    equals its host batch bit for bit even though a slow consumer is still reading slot k when slot k+1 uploads and slot k
+    is recycled two batches later; device buffers keep their addresses (CUDA-graph friendly)."""
+    from pea_diffusion_b200 import BatchStager
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(5)
+    host = [{"noisy_latents": torch.randn(4, 4, 64, 64, generator=g), "enc": torch.randn(4, 77, 1024, generator=g),
+             "timesteps": torch.randint(0, 1000, (4,), generator=g), "zh_or_not": torch.tensor([0, 1, 0, 1])} for _ in range(7)]
+    stager = BatchStager(dev, depth=depth, dtypes={"noisy_latents": torch.bfloat16})
+    big = torch.randn(4096, 4096, device=dev)
+    sums, ptrs = [], []
+    for b in stager.prefetch(host):
+        for _ in range(3):
+            big = (big @ big).clamp_(-1, 1)                      # keep the consumer stream busy before it reads the batch
+        sums.append((b["noisy_latents"].clone(), b["enc"].clone(), b["timesteps"].clone(), b["zh_or_not"].clone()))
+        ptrs.append(b["enc"].data_ptr())
+    torch.cuda.synchronize()
+    assert len(sums) == len(host)
+    for hb, (s, enc, t, zh) in zip(host, sums):
+        assert torch.equal(enc.cpu(), hb["enc"]) and torch.equal(t.cpu(), hb["timesteps"]) and torch.equal(zh.cpu(), hb["zh_or_not"])
+        assert s.dtype == torch.bfloat16 and torch.equal(s.cpu(), hb["noisy_latents"].to(torch.bfloat16))
+    assert len(set(ptrs)) == min(depth, len(host)) and ptrs[0] == ptrs[depth]
+    assert stager.h2d_bytes == 4 * 4 * 64 * 64 * 2 + 4 * 77 * 1024 * 4 + 4 * 8 + 4 * 8
+    assert list(stager.prefetch([])) == []

@@ -146,3 +146,10 @@ def test_bench_reference_arm_prints_one_json_line():
     assert d["impl"] == "reference" and d["metric"] == "SDXL-1024 KD train samples/s" and d["unit"] == "samples/s"
     assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["higher_is_better"] is True
+
+
+def test_batch_stager_needs_cuda():
+    from pea_diffusion_b200 import BatchStager
+    from pea_diffusion_b200._lib import PeaError
+    with pytest.raises(PeaError, match="no CPU fallback"):
+        BatchStager("cpu")
