@@ -11,15 +11,20 @@
 //                  S  = Q  K^T      SS  N80  K64   -> S[g]                    (g = tile parity)
 //                  dP = dO V^T      SS  N80  K64   -> dP[g]
 //                  dQ = dS K        TS  N64  K80   -> dQ      (A = dS, 16-bit, straight from TMEM over dP[g])
-//                  dV += P^T  dO    SS  N64  K128  -> dV      (A = P  from smem, MN-major; rows = keys)
-//                  dK += dS^T Q     SS  N64  K128  -> dK      (A = dS from smem, MN-major)
-//                dK / dV accumulate in TMEM across the CTA's consecutive tiles of one (batch, head).
+//                  dV^T += dO^T P   SS  M64 N80 K128 -> dKV lanes  0-15 of each quarter   (A = dO, B = P, both MN-major)
+//                  dK^T += Q^T  dS  SS  M64 N80 K128 -> dKV lanes 16-31 of each quarter   (A = Q,  B = dS)
+//                dK / dV are formed TRANSPOSED (rows = head dim, columns = keys): an M64 MMA fetches 2 KB of A + 2.5 KB of B
+//                per K=16 step where the M128 "rows = 128 padded keys" form fetched 4 KB + 2 KB, and shared-memory operand
+//                fetch is what bounds this kernel.  An M64 accumulator occupies lanes 0-15 of the four 32-lane quarters,
+//                so the second one interleaves into lanes 16-31 of the same 80 columns.  They accumulate in TMEM across
+//                the CTA's consecutive tiles of one (batch, head).
 //   warps 2..5   softmax group 0 (even tiles), warps 6..9 group 1 (odd tiles); thread = query row = TMEM lane:
 //                P = softmax(S), delta, dS = P o (dP - delta) * scale; P, dS -> shared memory (MN-major, 128B swizzle)
 //                and dS -> TMEM; later dQ TMEM -> 16-bit -> swizzled staging tile; on a (batch, head) change the
-//                group drains dK / dV (lane = key) and adds them to the fp32 accumulators in global memory.
+//                group drains dK^T / dV^T (lane = head-dim element, column = key) and adds them to the fp32 accumulators
+//                in global memory (16 consecutive floats per half warp and key).
 //   warp 10      dQ TMA-store issuer (so no softmax thread ever blocks on a store).
-// TMEM (512 columns): S[2] | dP[2] (160 each pair), dQ 64, dK 64, dV 64.
+// TMEM (512 columns): S[2] | dP[2] (160 each pair), dQ 64, dV^T / dK^T 80 (lane-interleaved).
 // Algorithmic bytes per tile: 2 x 16 KiB in (Q, dO) + 16 KiB out (dQ); FLOPs 10 x 128 x 80 x 64.
 #include "tc05.cuh"
 
@@ -30,7 +35,8 @@ constexpr int kQT = 128, kD = 64, kLP = 80;
 constexpr int kRing = 3;
 constexpr int kThreads = 352;
 constexpr uint32_t kTmemCols = 512;
-constexpr uint32_t kTS = 0, kTdP = 80, kTPair = 160, kTdQ = 320, kTdK = 384, kTdV = 448;
+constexpr uint32_t kTS = 0, kTdP = 80, kTPair = 160, kTdQ = 320, kTdKV = 384;
+constexpr uint32_t kLaneDK = 16u << 16;        // dK^T sits 16 lanes below dV^T in every quarter
 constexpr uint32_t kTile = kQT * kD * 2;        // 16 KiB: one Q / dO / dQ tile
 constexpr uint32_t kKV = kLP * kD * 2;          // 10 KiB: K or V
 constexpr uint32_t kSlab = kQT * 128;           // 16 KiB: [128 q][64 keys] slab of P / dS
@@ -206,12 +212,12 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_bwd_tc_kernel(const __grid_
         for (int k = 0; k < kLP / 16; ++k)
           tc::mma_f16_ts(tmem + kTdQ, tds + k * 8, kDescMN | (uint64_t)(ka + k * 128), p.idesc_dq, k > 0);
         tc::mma_commit(smem_u32(&dq_full));
-        // dV += P^T dO ; dK += dS^T Q   (reduction over the 128 query rows; the two chains interleaved)
+        // dV^T += dO^T P ; dK^T += Q^T dS   (reduction over the 128 query rows; the two chains interleaved)
 #pragma unroll
         for (int k = 0; k < kQT / 16; ++k) {
-          tc::mma_f16_ss(tmem + kTdV, kDescMN | (uint64_t)(pa + k * 128), kDescMN | (uint64_t)(doa + k * 128), p.idesc_dkv,
+          tc::mma_f16_ss(tmem + kTdKV, kDescMN | (uint64_t)(doa + k * 128), kDescMN | (uint64_t)(pa + k * 128), p.idesc_dkv,
                          (k > 0) ? 1u : (uint32_t)!first_of_bh);
-          tc::mma_f16_ss(tmem + kTdK, kDescMN | (uint64_t)(dsa + k * 128), kDescMN | (uint64_t)(qa + k * 128), p.idesc_dkv,
+          tc::mma_f16_ss(tmem + kTdKV + kLaneDK, kDescMN | (uint64_t)(qa + k * 128), kDescMN | (uint64_t)(dsa + k * 128), p.idesc_dkv,
                          (k > 0) ? 1u : (uint32_t)!first_of_bh);
         }
         tc::mma_commit(smem_u32(&pds_free));            // P / dS shared-memory tiles reusable
@@ -294,6 +300,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_bwd_tc_kernel(const __grid_
 #pragma unroll
       for (int j = 0; j < kLP; ++j) s4[j & 3] += e[j];
       const float inv = 1.0f / ((s4[0] + s4[1]) + (s4[2] + s4[3]));
+      TRACE(2 + g, t, 8);
 
       // ---- pass B: delta = sum_j P_j dP_j.  TMEM loads are software-pipelined: chunk c+1 is in flight while chunk c
       //      is consumed (tcgen05.wait::ld right after every load would expose its full latency ten times per tile).
@@ -311,6 +318,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_bwd_tc_kernel(const __grid_
         tc::tmem_ld_wait();
       }
       const float delta = ((d4[0] + d4[1]) + (d4[2] + d4[3])) * inv;
+      TRACE(2 + g, t, 9);
 
       // ---- pass C: dS = P o (dP - delta) * scale, P: 16-bit pairs in registers; dS -> TMEM over dP -------------------
       const float ps = inv * scale;
@@ -378,33 +386,31 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_bwd_tc_kernel(const __grid_
       if (lane == 0) { tc::mbar_arrive(smem_u32(&dq_free)); tc::mbar_arrive(smem_u32(&dq_staged)); }
       TRACE(2 + g, t, 7);
 
-      // ---- (batch, head) boundary: drain dK / dV (lane = key) and add them to the global fp32 accumulators ----------
+      // ---- (batch, head) boundary: drain dV^T | dK^T (lane = head-dim element) into the global fp32 accumulators -----
       if (flush) {
         tc::mbar_wait(smem_u32(&dkv_full), (uint32_t)flushes & 1u);
         tc::fence_after_sync();
-        uint32_t kk[64], vv[64];
+        uint32_t acc[kLP];
         {
-          uint32_t(&k0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&kk[0]);
-          uint32_t(&k1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&kk[32]);
-          uint32_t(&v0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&vv[0]);
-          uint32_t(&v1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&vv[32]);
-          tc::tmem_ld32(tmem + kTdK + lane_off, k0); tc::tmem_ld32(tmem + kTdK + lane_off + 32, k1);
-          tc::tmem_ld32(tmem + kTdV + lane_off, v0); tc::tmem_ld32(tmem + kTdV + lane_off + 32, v1);
+          uint32_t(&a0)[16] = *reinterpret_cast<uint32_t(*)[16]>(&acc[0]);
+          uint32_t(&a1)[16] = *reinterpret_cast<uint32_t(*)[16]>(&acc[16]);
+          uint32_t(&a2)[16] = *reinterpret_cast<uint32_t(*)[16]>(&acc[32]);
+          uint32_t(&a3)[16] = *reinterpret_cast<uint32_t(*)[16]>(&acc[48]);
+          uint32_t(&a4)[16] = *reinterpret_cast<uint32_t(*)[16]>(&acc[64]);
+          const uint32_t ta = tmem + kTdKV + lane_off;
+          tc::tmem_ld16(ta + 0, a0); tc::tmem_ld16(ta + 16, a1); tc::tmem_ld16(ta + 32, a2);
+          tc::tmem_ld16(ta + 48, a3); tc::tmem_ld16(ta + 64, a4);
           tc::tmem_ld_wait();
         }
         tc::fence_before_sync();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(smem_u32(&dkv_free));    // TMEM dK / dV may be overwritten by the next head
-        if (row < L) {
-          float* dkp = p.dk + (long long)b * p.bs_dkv + (long long)row * p.ld_dkv + h * kD;
-          float* dvp = p.dv + (long long)b * p.bs_dkv + (long long)row * p.ld_dkv + h * kD;
+        {
+          // quarter q holds rows 16q .. 16q+15 of dV^T in lanes 0-15 and of dK^T in lanes 16-31
+          float* base = (lane < 16 ? p.dv : p.dk) + (long long)b * p.bs_dkv + h * kD + q * 16 + (lane & 15);
 #pragma unroll
-          for (int d = 0; d < kD; d += 4) {
-            atomicAdd(reinterpret_cast<float4*>(dkp + d), make_float4(__uint_as_float(kk[d]), __uint_as_float(kk[d + 1]),
-                                                                       __uint_as_float(kk[d + 2]), __uint_as_float(kk[d + 3])));
-            atomicAdd(reinterpret_cast<float4*>(dvp + d), make_float4(__uint_as_float(vv[d]), __uint_as_float(vv[d + 1]),
-                                                                       __uint_as_float(vv[d + 2]), __uint_as_float(vv[d + 3])));
-          }
+          for (int key = 0; key < kLP; ++key)
+            if (key < L) atomicAdd(base + (long long)key * p.ld_dkv, __uint_as_float(acc[key]));
         }
         ++flushes;
       }
@@ -499,7 +505,7 @@ int attn2_bwd_tc(const pea_attn2_desc* a, cudaStream_t st) {
   const int fmt = fp16 ? 0 : 1;
   p.idesc_s = tc::make_idesc(fmt, 128, kLP, 0, 0);
   p.idesc_dq = tc::make_idesc(fmt, 128, kD, 0, 1);
-  p.idesc_dkv = tc::make_idesc(fmt, 128, kD, 1, 1);
+  p.idesc_dkv = tc::make_idesc(fmt, 64, kLP, 1, 1);
   p.dk = a->d_dk; p.dv = a->d_dv; p.ld_dkv = a->ld_dkv; p.bs_dkv = a->bs_dkv;
   p.vec_atomics = 1;
   return fp16 ? launch_bwd_tc<__half>(p, ctas, st) : launch_bwd_tc<__nv_bfloat16>(p, ctas, st);

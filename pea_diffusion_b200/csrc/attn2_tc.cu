@@ -205,8 +205,12 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_fwd_tc_kernel(const __grid_
     if (ntiles > 0) issue_s(0);
     if (ntiles > 1) issue_s(1);
     for (int t = 0; t < ntiles; ++t) {
-      if (t + 2 < ntiles) issue_s(t + 2);
       const int bh = (item0 + t) / tpb, j = t % kGroups;
+      // With one tile per (batch, head) -- three different heads in tiles t, t+1, t+2 -- the K|V buffer S(t+2) needs is the
+      // one P V(t) still reads: its load waits for kv_empty, which P V(t) commits, so S(t+2) must then follow P V(t).
+      const bool s_ahead = t + 2 < ntiles;
+      const bool s_after = s_ahead && (item0 + t + 2) / tpb != (item0 + t + 1) / tpb && (item0 + t + 1) / tpb != bh;
+      if (s_ahead && !s_after) issue_s(t + 2);
       if (bh != o_bh) { o_bh = bh; ++o_kvn; }
       const int kb = (o_kvn - 1) & 1;
       const bool last_of_bh = (t + 1 < ntiles) && ((item0 + t + 1) / tpb != bh);
@@ -225,6 +229,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_fwd_tc_kernel(const __grid_
         if (last_of_bh) tc::mma_commit(smem_u32(&kv_empty[kb]));   // K|V buffer reusable once these MMAs have read it
       }
       __syncwarp();
+      if (s_after) issue_s(t + 2);
     }
   } else {
     // ===== softmax + epilogue groups: warp w owns TMEM lanes [32*(w%4), +32); thread = query row =====

@@ -29,10 +29,12 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug traps (-> a CUDA error the host reports) instead of hanging the GPU box.
+// Bounded wait: a protocol bug traps (-> a CUDA error the host reports) instead of hanging the GPU box.  One try_wait
+// suspends for up to a few microseconds, so 2^20 spins is between ~50 ms and ~4 s -- every legitimate wait here is far
+// shorter.  (A clock64()-based bound was measured 5 % slower on the attention kernels: keep the loop minimal.)
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin)
-    if (spin > (1u << 26)) __trap();
+    if (spin > (1u << 20)) __trap();
 }
 
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }

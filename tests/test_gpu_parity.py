@@ -136,6 +136,7 @@ def _attn_case(B, N, L, H, d, dtype, seed=0, scale_q=1.0):
     (1, 4096, 77, 10, 64),   # SDXL 64x64 blocks
     (2, 1000, 52, 10, 64),   # ragged N, cn_clip default context length
     (2, 64, 64, 5, 64), (3, 16, 32, 4, 64), (1, 70, 1, 2, 64), (1, 130, 80, 2, 64),
+    (40, 100, 77, 20, 64),   # one tile per head, 6 heads per CTA: K|V double buffer turns over inside the producer's early loads
     (2, 1024, 77, 8, 40), (2, 256, 77, 8, 80), (2, 64, 77, 8, 160), (2, 16, 77, 8, 160),   # SD1.5 head sizes
 ])
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Per-tile event timeline of attn2_bwd_tc_kernel (CTA 0) from an instrumented build (-DPEA_TRACE):
-    PEA_B200_LIB=build/libpea_trace.so python tools/trace_bwd.py [N] [C]
+    sh tools/build_trace.sh && PEA_B200_LIB=build/libpea_trace.so python tools/trace_bwd.py [N] [C]
 """
 import ctypes as C
 import os
@@ -39,4 +39,6 @@ for t in range(lo, hi):
     row.append("| mma " + " ".join(f"{names[1][i]}={ev(1, t, i) - t0:7d}" for i in range(5)))
     row.append("| sm " + " ".join(f"{names[2][i]}={ev(2 + g, t, i) - t0:7d}" for i in range(8)))
     print(" ".join(row))
+print("softmax passes A / B / C (cycles):", [(ev(2 + (t & 1), t, 8) - ev(2 + (t & 1), t, 1), ev(2 + (t & 1), t, 9) - ev(2 + (t & 1), t, 8),
+                                               ev(2 + (t & 1), t, 2) - ev(2 + (t & 1), t, 9)) for t in range(lo, hi)])
 print("per-tile period (MMA ds_ready to ds_ready):", [ev(1, t + 1, 3) - ev(1, t, 3) for t in range(lo, hi - 1)])
