@@ -97,6 +97,26 @@ def to_device(hbatch, dev):
     return {k: v.to(dev, non_blocking=True) for k, v in hbatch.items()}
 
 
+def event_pair_overhead_us(dev, n=200):
+    """Median elapsed time of a CUDA-event pair around the library's smallest launch (pea_cfg_select on 8 elements): what
+    event bracketing adds to every per-launch figure (record + launch latency + a ~2 us minimal kernel).  Reported next
+    to the raw roofline numbers; never subtracted from `achieved` / `frac`."""
+    import torch
+    from pea_diffusion_b200 import ops
+    m = torch.zeros(1, dtype=torch.uint8, device=dev)
+    a = torch.zeros(1, 8, dtype=torch.bfloat16, device=dev)
+    pairs = []
+    for _ in range(n):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ops.cfg_select(m, a, a)
+        e1.record()
+        pairs.append((e0, e1))
+    torch.cuda.synchronize()
+    t = sorted(e0.elapsed_time(e1) for e0, e1 in pairs)
+    return t[len(t) // 2] * 1e3
+
+
 # ------------------------------------------------------------------------------------------------- clocks
 class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -305,6 +325,7 @@ def main():
         launches = (_lib.launch_count() - n0) * args.steps // prof_steps
     ksum = ops.TIMER.summary()
     ops.TIMER.reset(False)
+    ev_overhead_us = event_pair_overhead_us(dev)
 
     # ---- e2e: pinned host inputs -> H2D every step, loss read back D2H every step -------------------------------
     host_loss = torch.empty(4, dtype=torch.float32).pin_memory()
@@ -352,6 +373,8 @@ def main():
         "roofline": {"bound": "hbm", "kernel": "attn2 fused forward + backward (all 70 layers x student fwd/bwd + teacher fwd)",
                      "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
                      "traffic": None, "peak_source": pk_kind,
+                     "event_pair_overhead_us": ev_overhead_us,
+                     "frac_net_of_event_overhead": (a_bytes / (max(a_ms - ev_overhead_us * 1e-3 * (at["attn2_fwd"]["launches"] + at["attn2_bwd"]["launches"]), 1e-9) * 1e-3) / 1e9 / pk["hbm_gbs"]) if a_ms > 0 else 0.0,
                      "timing": ("CUDA events around every launch of %d eager steps run right after the graph-replayed timed region "
                                 "(events cannot bracket nodes inside a CUDA graph)" % prof_steps) if graph_mode else
                                "CUDA events around every launch inside the timed steps",

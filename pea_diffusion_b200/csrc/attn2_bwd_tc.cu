@@ -257,8 +257,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_bwd_tc_kernel(const __grid_
       TRACE(2 + g, t, 1);
       tc::fence_after_sync();
 
-      // Columns >= L hold S = 0 (K rows beyond L are zero-filled), never NaN: only the chunk that straddles L needs
-      // masking, and "(c + 1) * 16 <= L" is warp-uniform.
+      // Columns >= L hold S = 0 (K rows beyond L are zero-filled), never NaN.
       // ---- pass A: S -> e = exp2((s - max) * scale * log2 e), row sum ---------------------------------------------
       float e[kLP];
       {
@@ -271,30 +270,22 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_bwd_tc_kernel(const __grid_
         tc::tmem_ld16(t_s + 0, c0); tc::tmem_ld16(t_s + 16, c1); tc::tmem_ld16(t_s + 32, c2);
         tc::tmem_ld16(t_s + 48, c3); tc::tmem_ld16(t_s + 64, c4);
         tc::tmem_ld_wait();
+        // keys >= L -> -inf once (see attn2_tc.cu): max / exp below then exist in one unmasked copy; exp2(-inf) = 0
+#pragma unroll
+        for (int c = 0; c < kLP / 16; ++c) {
+          if ((c + 1) * 16 > L) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) sv[c * 16 + j] = c * 16 + j < L ? sv[c * 16 + j] : 0xff800000u;
+          }
+        }
         // four independent chains: a single softmax warp per scheduler cannot hide a serial 80-long dependency chain
         float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-        for (int c = 0; c < kLP / 16; ++c) {
-          if ((c + 1) * 16 <= L) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) m4[j & 3] = fmaxf(m4[j & 3], __uint_as_float(sv[c * 16 + j]));
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) m4[j & 3] = fmaxf(m4[j & 3], c * 16 + j < L ? __uint_as_float(sv[c * 16 + j]) : -INFINITY);
-          }
-        }
+        for (int j = 0; j < kLP; ++j) m4[j & 3] = fmaxf(m4[j & 3], __uint_as_float(sv[j]));
         const float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
         const float off = m * sl2;
 #pragma unroll
-        for (int c = 0; c < kLP / 16; ++c) {
-          if ((c + 1) * 16 <= L) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) e[c * 16 + j] = ex2(fmaf(__uint_as_float(sv[c * 16 + j]), sl2, -off));
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) e[c * 16 + j] = c * 16 + j < L ? ex2(fmaf(__uint_as_float(sv[c * 16 + j]), sl2, -off)) : 0.f;
-          }
-        }
+        for (int j = 0; j < kLP; ++j) e[j] = ex2(fmaf(__uint_as_float(sv[j]), sl2, -off));
       }
       float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -321,7 +312,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_bwd_tc_kernel(const __grid_
       TRACE(2 + g, t, 9);
 
       // ---- pass C: dS = P o (dP - delta) * scale, P: 16-bit pairs in registers; dS -> TMEM over dP -------------------
-      const float ps = inv * scale;
+      const float nds = -delta * scale;   // dS = P * (dP * scale - delta * scale): one FFMA + one FMUL per element
       uint32_t pp[kLP / 2], dd[kLP / 2];
 #pragma unroll
       for (int c = 0; c < kLP / 16; ++c) {
@@ -331,9 +322,9 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_bwd_tc_kernel(const __grid_
         if (c + 1 < kLP / 16) tc::tmem_ld16(t_dp + (c + 1) * 16, nxt);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float e0 = e[c * 16 + 2 * j], e1 = e[c * 16 + 2 * j + 1];
-          pp[c * 8 + j] = pack2<T>(e0 * inv, e1 * inv);
-          dd[c * 8 + j] = pack2<T>(e0 * ps * (__uint_as_float(cur[2 * j]) - delta), e1 * ps * (__uint_as_float(cur[2 * j + 1]) - delta));
+          const float p0 = e[c * 16 + 2 * j] * inv, p1 = e[c * 16 + 2 * j + 1] * inv;
+          pp[c * 8 + j] = pack2<T>(p0, p1);
+          dd[c * 8 + j] = pack2<T>(p0 * fmaf(__uint_as_float(cur[2 * j]), scale, nds), p1 * fmaf(__uint_as_float(cur[2 * j + 1]), scale, nds));
         }
         if (c + 1 < kLP / 16) tc::tmem_ld_wait();   // chunk c+1 (columns >= 16(c+1)) is in registers before columns [8c, 8c+8) are overwritten
         uint32_t(&d8)[8] = *reinterpret_cast<uint32_t(*)[8]>(&dd[c * 8]);
@@ -407,10 +398,13 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_bwd_tc_kernel(const __grid_
         if (lane == 0) tc::mbar_arrive(smem_u32(&dkv_free));    // TMEM dK / dV may be overwritten by the next head
         {
           // quarter q holds rows 16q .. 16q+15 of dV^T in lanes 0-15 and of dK^T in lanes 16-31
-          float* base = (lane < 16 ? p.dv : p.dk) + (long long)b * p.bs_dkv + h * kD + q * 16 + (lane & 15);
+          float* ptr = (lane < 16 ? p.dv : p.dk) + (long long)b * p.bs_dkv + h * kD + q * 16 + (lane & 15);
+          const long long ld = p.ld_dkv;
 #pragma unroll
-          for (int key = 0; key < kLP; ++key)
-            if (key < L) atomicAdd(base + (long long)key * p.ld_dkv, __uint_as_float(acc[key]));
+          for (int key = 0; key < kLP; ++key) {     // running pointer: 3-4 instructions per key instead of a 64-bit multiply each
+            if (key < L) atomicAdd(ptr, __uint_as_float(acc[key]));
+            ptr += ld;
+          }
         }
         ++flushes;
       }

@@ -88,6 +88,13 @@ __device__ __forceinline__ void load8(const void* base, int dtype, long long off
   }
 }
 
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
+}
+
 __device__ __forceinline__ void store8(void* base, int dtype, long long off, bool vec, int valid, const float* f, int mode) {
   if (dtype == PEA_F32) {
     float* p = static_cast<float*>(base) + off;
@@ -158,21 +165,23 @@ template <int BN>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tacc, int row, int n0, bool al0, bool al1, bool alx) {
   const bool row_ok = row < p.M;
   const float* radd = (p.rowadd && row_ok) ? p.rowadd + (long long)(row / p.rowadd_group) * p.N : nullptr;
+  // ONE rolled copy of the 8-column body.  With every dtype / mode variant inlined it is ~1.5 k instructions; unrolled four
+  // times it made the kernel 112 KB of code, more than the 32 KB instruction cache, and a one-tile-per-CTA GEMM (the adapter
+  // shapes) spent most of its 22 us fetching epilogue instructions (ncu r1: 42 k cycles for 16 k-blocks).  The TMEM load of
+  // the next 8 columns is issued before the current ones are processed, so its latency stays hidden.
+  uint32_t v[8];
+  tmem_ld8(tacc, v);
 #pragma unroll 1
-  for (int c = 0; c < BN / 32; ++c) {
-    uint32_t v[32];
-    tc::tmem_ld32(tacc + (uint32_t)(c * 32), v);
+  for (int c = 0; c < BN / 8; ++c) {
     tc::tmem_ld_wait();
-    if (!row_ok) continue;
+    float f[8];
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      const int n = n0 + c * 32 + g * 8;
-      if (n >= p.N) break;
+    for (int j = 0; j < 8; ++j) f[j] = p.alpha * __uint_as_float(v[j]);
+    if (c + 1 < BN / 8) tmem_ld8(tacc + (uint32_t)((c + 1) * 8), v);   // warp-uniform: all 32 lanes issue it
+    const int n = n0 + c * 8;
+    if (row_ok && n < p.N) {
       const int valid = min(8, p.N - n);
       const bool full = valid == 8;
-      float f[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = p.alpha * __uint_as_float(v[g * 8 + j]);
       if (p.bias) {
 #pragma unroll
         for (int j = 0; j < 8; ++j)
@@ -195,6 +204,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tacc
 #pragma unroll
           for (int j = 0; j < 8; ++j) f[j] = gelu_exact(f[j]);
         }
+#pragma unroll 1
         for (int s = 0; s < p.out1_nsplit; ++s) {
           float r[8];
 #pragma unroll
