@@ -54,7 +54,6 @@ struct BwdParams {
   float scale_log2, scale;
   uint32_t idesc_s, idesc_dq, idesc_dkv;
   float* dk; float* dv; long long ld_dkv, bs_dkv;
-  int vec_atomics;
 };
 
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
@@ -463,8 +462,8 @@ bool attn2_bwd_tc_eligible(const pea_attn2_desc* a) {
   const int C = a->H * a->d;
   auto al16 = [](const void* x) { return (reinterpret_cast<uintptr_t>(x) & 15) == 0; };
   return voff >= C && voff + C <= a->ld_kv && voff % 8 == 0 && a->ld_q % 8 == 0 && a->ld_do % 8 == 0 && a->ld_dq % 8 == 0 &&
-         a->ld_kv % 8 == 0 && a->bs_kv % 8 == 0 && al16(a->d_q) && al16(a->d_k) && al16(a->d_do) && al16(a->d_dq) &&
-         a->ld_dkv % 4 == 0 && a->bs_dkv % 4 == 0 && al16(a->d_dk) && al16(a->d_dv);   // float4 atomics on dK / dV
+         a->ld_kv % 8 == 0 && a->bs_kv % 8 == 0 && al16(a->d_q) && al16(a->d_k) && al16(a->d_do) && al16(a->d_dq);
+  // dK / dV are fp32 accumulators updated with scalar red.global.add.f32: no layout constraint beyond the ABI's
 }
 
 int attn2_bwd_tc(const pea_attn2_desc* a, cudaStream_t st) {
@@ -501,7 +500,6 @@ int attn2_bwd_tc(const pea_attn2_desc* a, cudaStream_t st) {
   p.idesc_dq = tc::make_idesc(fmt, 128, kD, 0, 1);
   p.idesc_dkv = tc::make_idesc(fmt, 64, kLP, 1, 1);
   p.dk = a->d_dk; p.dv = a->d_dv; p.ld_dkv = a->ld_dkv; p.bs_dkv = a->bs_dkv;
-  p.vec_atomics = 1;
   return fp16 ? launch_bwd_tc<__half>(p, ctas, st) : launch_bwd_tc<__nv_bfloat16>(p, ctas, st);
 }
 

@@ -537,6 +537,24 @@ def test_group_projection_matches_per_layer_path():
     assert rel_err(res[1][1], res[0][1]) < 3e-2
 
 
+@pytest.mark.gpu
+def test_attn2_bwd_accumulates_into_odd_stride_view(ops):
+    """dK|dV land in a caller-owned fp32 view and are ADDED to what is there (the shared buffer of Attn2Group); the tcgen05
+    path uses scalar reductions, so a row stride that is not a multiple of 4 floats must work and stay on that path."""
+    B, N, L, H, d = 2, 512, 77, 4, 64
+    C = H * d
+    q, kv, do = _attn_case(B, N, L, H, d, torch.bfloat16, seed=11, scale_q=2.0)
+    dq_ref, dkv_ref = ops.attn2_bwd(q.to(DEV), kv.to(DEV), do.to(DEV), H, d ** -0.5)
+    big = torch.full((B, L, 2 * C + 3), 0.5, device=DEV, dtype=torch.float32)
+    view = big[:, :, 1:1 + 2 * C]
+    assert view.stride(1) % 4 != 0
+    dq, out = ops.attn2_bwd(q.to(DEV), kv.to(DEV), do.to(DEV), H, d ** -0.5, dkv=view)
+    assert out.data_ptr() == view.data_ptr()
+    assert torch.equal(dq, dq_ref)
+    assert rel_err(view - 0.5, dkv_ref) < 1e-5           # same kernel, different atomic order only
+    assert float(big[:, :, 0].min()) == 0.5 and float(big[:, :, -2:].max()) == 0.5   # nothing outside the view touched
+
+
 # ------------------------------------------------------------------------------------------------- input staging (N4)
 
 @pytest.mark.gpu
