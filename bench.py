@@ -97,23 +97,72 @@ def to_device(hbatch, dev):
     return {k: v.to(dev, non_blocking=True) for k, v in hbatch.items()}
 
 
-def event_pair_overhead_us(dev, n=200):
-    """Median elapsed time of a CUDA-event pair around the library's smallest launch (pea_cfg_select on 8 elements): what
-    event bracketing adds to every per-launch figure (record + launch latency + a ~2 us minimal kernel).  Reported next
-    to the raw roofline numbers; never subtracted from `achieved` / `frac`."""
+def profile_in_graph(trainer, adapter, replays):
+    """Capture trainer._forward_backward into a fresh CUDA graph with ops.TIMER in external-event mode, replay it
+    ``replays`` times and return ({kernel: {launches, ms, bytes, flops}} summed over the replays, graph keep-alive)."""
+    import torch
+    from pea_diffusion_b200 import ops
+    params = list(adapter.parameters())
+    saved = [q.grad for q in params]                    # the trainer's own graph writes into these: keep them attached
+    for q in params:
+        q.grad = None
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    total = {}
+    g = torch.cuda.CUDAGraph()
+    try:
+        ops.TIMER.reset(True, external=True)
+        with torch.cuda.graph(g, stream=side):
+            trainer._forward_backward(trainer._static_in)
+        ops.TIMER.enabled = False
+        for _ in range(replays):
+            g.replay()
+            torch.cuda.synchronize()
+            for name, r in ops.TIMER.summary().items():
+                t = total.setdefault(name, {"launches": 0, "ms": 0.0, "bytes": 0, "flops": 0})
+                for k in t:
+                    t[k] += r[k]
+    finally:
+        ops.TIMER.reset(False)
+        for q, g_ in zip(params, saved):
+            q.grad = g_
+    return total, g
+
+
+def event_pair_overhead_us(dev, in_graph, n=100):
+    """Median elapsed time of a CUDA-event pair around the library's smallest launch (pea_cfg_select on 8 elements),
+    taken the same way as the per-kernel figures (event-record nodes inside a replayed CUDA graph, or eager): what the
+    bracketing itself adds to every per-launch time (record + launch latency + a ~2 us minimal kernel).  Reported next to
+    the raw roofline numbers; never subtracted from `achieved` / `frac`."""
     import torch
     from pea_diffusion_b200 import ops
     m = torch.zeros(1, dtype=torch.uint8, device=dev)
     a = torch.zeros(1, 8, dtype=torch.bfloat16, device=dev)
+    out = ops.cfg_select(m, a, a)   # warm-up (and the output buffer the captured launches reuse)
     pairs = []
-    for _ in range(n):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        ops.cfg_select(m, a, a)
-        e1.record()
-        pairs.append((e0, e1))
+
+    def body():
+        for _ in range(n):
+            e0 = torch.cuda.Event(enable_timing=True, external=in_graph)
+            e1 = torch.cuda.Event(enable_timing=True, external=in_graph)
+            e0.record()
+            ops.cfg_select(m, a, a)
+            e1.record()
+            pairs.append((e0, e1))
+
+    if in_graph:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            body()
+        g.replay()
+        g.replay()
+    else:
+        body()
     torch.cuda.synchronize()
     t = sorted(e0.elapsed_time(e1) for e0, e1 in pairs)
+    del out
     return t[len(t) // 2] * 1e3
 
 
@@ -325,7 +374,27 @@ def main():
         launches = (_lib.launch_count() - n0) * args.steps // prof_steps
     ksum = ops.TIMER.summary()
     ops.TIMER.reset(False)
-    ev_overhead_us = event_pair_overhead_us(dev)
+    timing_note = ("CUDA events around every launch of %d eager steps run right after the graph-replayed timed region"
+                   % prof_steps) if graph_mode else "CUDA events around every launch inside the timed steps"
+    if graph_mode and not args.timed_only:
+        # Per-kernel times INSIDE a replayed step: capture the same forward+backward once more with external events
+        # (event-record nodes) around every launch of the library, replay it, read the events after each replay.  The
+        # eager figures above carry ~5-10 us of host launch latency per bracket; these do not.
+        try:
+            g_steps = min(args.steps, 5)
+            ksum_g, _keep = profile_in_graph(trainer, adapter, g_steps)
+            if ksum_g.get("attn2_fwd", {}).get("launches", 0) > 0:
+                ksum, prof_steps = ksum_g, g_steps
+                timing_note = ("CUDA events recorded as event-record nodes around every launch inside %d replays of a CUDA graph of "
+                               "the same forward+backward, captured and replayed right after the timed region" % g_steps)
+            del _keep
+        except Exception as exc:  # keep the eager figures; say why
+            timing_note += " (in-graph event timing failed: %s)" % (str(exc).splitlines()[0][:160] if str(exc) else type(exc).__name__)
+        torch.cuda.empty_cache()
+    try:
+        ev_overhead_us = event_pair_overhead_us(dev, in_graph=timing_note.startswith("CUDA events recorded as event-record nodes"))
+    except Exception:
+        ev_overhead_us = None
 
     # ---- e2e: pinned host inputs -> H2D every step, loss read back D2H every step -------------------------------
     host_loss = torch.empty(4, dtype=torch.float32).pin_memory()
@@ -374,10 +443,8 @@ def main():
                      "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
                      "traffic": None, "peak_source": pk_kind,
                      "event_pair_overhead_us": ev_overhead_us,
-                     "frac_net_of_event_overhead": (a_bytes / (max(a_ms - ev_overhead_us * 1e-3 * (at["attn2_fwd"]["launches"] + at["attn2_bwd"]["launches"]), 1e-9) * 1e-3) / 1e9 / pk["hbm_gbs"]) if a_ms > 0 else 0.0,
-                     "timing": ("CUDA events around every launch of %d eager steps run right after the graph-replayed timed region "
-                                "(events cannot bracket nodes inside a CUDA graph)" % prof_steps) if graph_mode else
-                               "CUDA events around every launch inside the timed steps",
+                     "frac_net_of_event_overhead": (a_bytes / (max(a_ms - ev_overhead_us * 1e-3 * (at["attn2_fwd"]["launches"] + at["attn2_bwd"]["launches"]), 1e-9) * 1e-3) / 1e9 / pk["hbm_gbs"]) if (a_ms > 0 and ev_overhead_us is not None) else None,
+                     "timing": timing_note,
                      "per_kernel": per_kernel},
     }
     if not args.no_cpu_baseline and world == 1:

@@ -23,10 +23,14 @@ class KernelTimer:
 
     def __init__(self):
         self.enabled = False
+        self.external = False
         self.records = []  # (name, algorithmic_bytes, flops, start_event, end_event)
 
-    def reset(self, enabled: bool) -> None:
+    def reset(self, enabled: bool, external: bool = False) -> None:
+        """``external=True``: the events become event-record NODES when the launches are captured into a CUDA graph, so
+        every replay of that graph re-records them and the kernels can be timed inside the replayed step."""
         self.enabled = enabled
+        self.external = external
         self.records = []
 
     def summary(self):
@@ -50,13 +54,13 @@ class _timed:
 
     def __enter__(self):
         if TIMER.enabled:
-            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0 = torch.cuda.Event(enable_timing=True, external=True) if TIMER.external else torch.cuda.Event(enable_timing=True)
             self.e0.record()
         return self
 
     def __exit__(self, *exc):
         if TIMER.enabled:
-            e1 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True, external=True) if TIMER.external else torch.cuda.Event(enable_timing=True)
             e1.record()
             TIMER.records.append((*self.args, self.e0, e1))
         return False
