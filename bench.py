@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--adapter-precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager step instead of the CUDA-graph replay")
+    ap.add_argument("--overlap-teacher", type=int, default=0, help="1: teacher forward on its own stream, concurrent with the student forward")
     ap.add_argument("--timed-only", action="store_true", help="skip the eager per-kernel pass and the e2e loop (ncu launch-list runs)")
     ap.add_argument("--tiny", action="store_true", help="tiny shell (debug only; the JSON line says so)")
     return ap.parse_args()
@@ -313,7 +314,7 @@ def main():
     attn2.install(student, freeze=True)
     attn2.install(teacher, freeze=True)
     adapter = A.MLP(in_dim, pooled, hidden, cfg.cross_attention_dim, False, precision=args.adapter_precision).to(dev)
-    trainer = KDTrainer(student, teacher, adapter, "sdxl", lr=1e-5, cuda_graph=not args.no_graph)
+    trainer = KDTrainer(student, teacher, adapter, "sdxl", lr=1e-5, cuda_graph=not args.no_graph, overlap_teacher=bool(args.overlap_teacher))
 
     B = args.batch
     hbatch = host_stage(synth_batch(B, latent, cfg, in_dim, 1234 + rank), act)
@@ -433,7 +434,8 @@ def main():
                                 "train_sdxl_zh.py KD step, random-init SDXL UNet shell x2 (student+teacher), 1024px "
                                 f"({latent}x{latent} latent), bf16, batch {B}/GPU, teacher+student forward, backward to the 6.03M adapter, AdamW"),
                    "global_batch": world * B, "parallelism": f"dp{world}", "adapter_precision": args.adapter_precision,
-                   "step_execution": "CUDA graph replay (fwd+bwd captured once) + eager all-reduce/AdamW" if graph_mode else "eager",
+                   "step_execution": ("CUDA graph replay (fwd+bwd captured once) + eager all-reduce/AdamW" if graph_mode else "eager") +
+                                     ("; teacher forward on a parallel stream / graph branch" if args.overlap_teacher else ""),
                    "l2": "no explicit flush: every step streams 10.3 GB of weights plus activations (>> 126 MB L2)"},
         "e2e": {"value": world * B / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 16,
                 "ms_per_step": ms_e2e},

@@ -75,11 +75,16 @@ class KDTaps:
 
 def kd_forward(student: nn.Module, teacher: nn.Module, adapter: nn.Module, batch: Mapping[str, Tensor], taps_s: KDTaps,
                taps_t: KDTaps, variant: str = "sdxl", feature_weight: float = 0.1,
-               skip_nonfinite: Optional[bool] = None) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+               skip_nonfinite: Optional[bool] = None, teacher_stream: Optional["torch.cuda.Stream"] = None
+               ) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
     """Forward graph of one KD step on device tensors; returns (loss, L0, L1, L2) without any host sync.
 
     ``batch`` keys: noisy_latents, noise, timesteps, enc, enc_uncond, teacher_ctx,
     teacher_ctx_uncond, zh_or_not, prompt_mask, and for SDXL teacher_pooled, time_ids.
+
+    ``teacher_stream``: run the teacher's forward (no_grad, independent of the adapter: train_sdxl_zh.py:410-415) on that
+    stream, concurrently with the student's forward, and join before the loss.  Inside a CUDA-graph capture this becomes
+    a parallel branch of the graph.  The result is identical; only the schedule changes.
     """
     if skip_nonfinite is None:
         skip_nonfinite = variant == "sd"
@@ -99,10 +104,24 @@ def kd_forward(student: nn.Module, teacher: nn.Module, adapter: nn.Module, batch
         kw_s = kw_t = None
     taps_s.clear()
     taps_t.clear()
-    pred = student(batch["noisy_latents"], batch["timesteps"], ctx, added_cond_kwargs=kw_s)[0]
-    with torch.no_grad():
-        t_ctx = cfg_dropout_select(mask, batch["teacher_ctx_uncond"], batch["teacher_ctx"])
-        pred_t = teacher(batch["noisy_latents"], batch["timesteps"], t_ctx, added_cond_kwargs=kw_t)[0]
+
+    def run_teacher():
+        with torch.no_grad():
+            t_ctx = cfg_dropout_select(mask, batch["teacher_ctx_uncond"], batch["teacher_ctx"])
+            return teacher(batch["noisy_latents"], batch["timesteps"], t_ctx, added_cond_kwargs=kw_t)[0]
+
+    if teacher_stream is not None:
+        main = torch.cuda.current_stream()
+        teacher_stream.wait_stream(main)           # batch tensors (and the previous step's readers of recycled memory)
+        with torch.cuda.stream(teacher_stream):
+            pred_t = run_teacher()
+        pred = student(batch["noisy_latents"], batch["timesteps"], ctx, added_cond_kwargs=kw_s)[0]
+        main.wait_stream(teacher_stream)           # join: the loss reads the teacher's prediction and taps
+        # No record_stream needed: teacher_stream allocates nothing more in this step, and its next use (next step) starts
+        # with wait_stream(main), i.e. after every main-stream reader of the tensors it produced here.
+    else:
+        pred = student(batch["noisy_latents"], batch["timesteps"], ctx, added_cond_kwargs=kw_s)[0]
+        pred_t = run_teacher()
     return kd_loss(pred, batch["noise"], pred_t, taps_s.tensors(), taps_t.tensors(), batch["zh_or_not"],
                    feature_weight=feature_weight, skip_nonfinite=skip_nonfinite)
 
@@ -172,7 +191,7 @@ class KDTrainer:
 
     def __init__(self, student: nn.Module, teacher: nn.Module, adapter: nn.Module, variant: str = "sdxl", lr: float = 1e-5,
                  betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0, feature_weight: float = 0.1,
-                 process_group=None, cuda_graph: bool = False):
+                 process_group=None, cuda_graph: bool = False, overlap_teacher: bool = False):
         self.student, self.teacher, self.adapter, self.variant = student, teacher, adapter, variant
         self.feature_weight = feature_weight
         self.taps_s, self.taps_t = KDTaps(student), KDTaps(teacher)
@@ -182,6 +201,8 @@ class KDTrainer:
         # group, so the effective decay is 0
         self.opt = torch.optim.AdamW(params, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, fused=fused)
         self.cuda_graph = cuda_graph
+        # teacher forward on its own stream, concurrent with the student forward (a parallel branch under cuda_graph)
+        self.teacher_stream = torch.cuda.Stream() if overlap_teacher and fused else None
         self.reducer = GradAllReducer(params, process_group, hooks=not cuda_graph)
         self._graph = None
         self._static_in: Dict[str, Tensor] = {}
@@ -189,7 +210,7 @@ class KDTrainer:
 
     def _forward_backward(self, batch: Mapping[str, Tensor]) -> Tensor:
         loss, l0, l1, l2 = kd_forward(self.student, self.teacher, self.adapter, batch, self.taps_s, self.taps_t, self.variant,
-                                      self.feature_weight)
+                                      self.feature_weight, teacher_stream=self.teacher_stream)
         loss.backward()
         self.taps_s.clear()
         self.taps_t.clear()
