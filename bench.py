@@ -440,6 +440,15 @@ def main():
     a_ms = at["attn2_fwd"]["ms"] + at["attn2_bwd"]["ms"]
     a_bytes = at["attn2_fwd"]["bytes"] + at["attn2_bwd"]["bytes"]
     achieved = a_bytes / (a_ms * 1e-3) / 1e9 if a_ms > 0 else 0.0
+    # DRAM traffic per launch (read + write) of the same launch mix, from the committed ncu --set full capture of the two
+    # shapes a step launches (profiles/r1_attn2_traffic.json); null on other workloads
+    traffic, traffic_src = None, None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_attn2_traffic.json")))
+        if not args.tiny and args.latent == 128 and args.batch == 8:
+            traffic, traffic_src = tj["traffic_bytes_per_launch_step_mix"], "profiles/r1_attn2_traffic.json (bytes per launch, step mix; algorithmic: %d)" % tj["algorithmic_bytes_per_launch_step_mix"]
+    except Exception:
+        pass
     per_kernel = {k: {"launches_per_step": v["launches"] / prof_steps, "ms_per_step": v["ms"] / prof_steps,
                       "GBps": (v["bytes"] / (v["ms"] * 1e-3) / 1e9 if v["ms"] > 0 else 0.0),
                       "TFLOPs": (v["flops"] / (v["ms"] * 1e-3) / 1e12 if v["ms"] > 0 else 0.0)} for k, v in at.items()}
@@ -461,7 +470,7 @@ def main():
         "clocks": clk,
         "roofline": {"bound": "hbm", "kernel": "attn2 fused forward + backward (all 70 layers x student fwd/bwd + teacher fwd)",
                      "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
-                     "traffic": None, "peak_source": pk_kind,
+                     "traffic": traffic, "traffic_source": traffic_src, "peak_source": pk_kind,
                      "event_pair_overhead_us": ev_overhead_us,
                      "frac_net_of_event_overhead": (a_bytes / (max(a_ms - ev_overhead_us * 1e-3 * (at["attn2_fwd"]["launches"] + at["attn2_bwd"]["launches"]), 1e-9) * 1e-3) / 1e9 / pk["hbm_gbs"]) if (a_ms > 0 and ev_overhead_us is not None) else None,
                      "timing": timing_note,
