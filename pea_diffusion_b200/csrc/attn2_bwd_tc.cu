@@ -91,6 +91,10 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_bwd_tc_kernel(const __grid_
   const int item0 = blockIdx.x * p.tiles_per_cta;
   const int ntiles = min(p.tiles_per_cta, p.total_tiles - item0);
   const int tpb = p.tiles_per_bh;
+  // Work items are consecutive: every role walks (batch, head, tile) with counters, and these are the kernel's only integer
+  // divisions (the MMA warp is one latency-bound instruction stream; see attn2_tc.cu).
+  const int bh0 = item0 / tpb, rem0 = item0 - bh0 * tpb;
+  const int b0 = bh0 / p.H, h0 = bh0 - b0 * p.H;
   if (warp == 0) TRACE(0, 63, 15);   // kernel entry
 
   if (warp == 0 && lane == 0) {
@@ -119,12 +123,11 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_bwd_tc_kernel(const __grid_
 
   if (warp == 0) {
     // ===== TMA producer =====
-    int cur_bh = -1, kv_n = 0;
+    int kv_n = 0, s = 0;
+    uint32_t ring_ph = 0;
+    int b = b0, h = h0, tile = rem0;
     for (int t = 0; t < ntiles; ++t) {
-      const int item = item0 + t;
-      const int bh = item / tpb, tile = item - bh * tpb;
-      const int b = bh / p.H, h = bh - b * p.H;
-      if (bh != cur_bh) {
+      if (t == 0 || tile == 0) {   // first tile of a (batch, head) in this CTA's range
         const int kb = kv_n & 1;
         tc::mbar_wait(smem_u32(&kv_empty[kb]), ((uint32_t)(kv_n >> 1) & 1u) ^ 1u);
         if (tc::elect_one()) {
@@ -134,11 +137,9 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_bwd_tc_kernel(const __grid_
           tc::tma_load_3d(smem + kOffKV + kb * 2 * kKV + kKV, &p.tmKV, bk, p.voff + h * kD, 0, b);
         }
         __syncwarp();
-        cur_bh = bh;
         ++kv_n;
       }
-      const int s = t % kRing;
-      tc::mbar_wait(smem_u32(&ring_empty[s]), ((uint32_t)(t / kRing) & 1u) ^ 1u);
+      tc::mbar_wait(smem_u32(&ring_empty[s]), ring_ph ^ 1u);
       TRACE(0, t, 0);
       if (tc::elect_one()) {
         const uint32_t fb = smem_u32(&ring_full[s]);
@@ -147,6 +148,8 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_bwd_tc_kernel(const __grid_
         tc::tma_load_3d(smem + kOffRing + s * 2 * kTile + kTile, &p.tmdO, fb, h * kD, tile * kQT, b);
       }
       __syncwarp();
+      if (++s == kRing) { s = 0; ring_ph ^= 1u; }
+      if (++tile == tpb) { tile = 0; if (++h == p.H) { h = 0; ++b; } }
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
@@ -155,19 +158,22 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_bwd_tc_kernel(const __grid_
     //                 P, dS as A ([q rows][keys], two 64-key slabs 16 KiB apart = LBO): K=16 step = 16 q rows = 2048 B.
     constexpr uint64_t kDescK = ((uint64_t)1 << 16) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
     constexpr uint64_t kDescMN = ((uint64_t)(kSlab >> 4) << 16) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
-    int s_bh = -1, s_kvn = 0;   // K|V bookkeeping of the S/dP stream (runs up to two tiles ahead)
-    int m_bh = -1, m_kvn = 0;   // ... and of the dQ/dK/dV stream
+    int s_pos = rem0, s_kvn = 0;   // tile-in-head position / K|V bookkeeping of the S/dP stream (runs up to two tiles ahead)
+    int m_pos = rem0, m_kvn = 0;   // ... and of the dQ/dK/dV stream
+    int s_rs = 0, m_rs = 0;        // ring slot (t % kRing) of either stream, as counters
+    uint32_t s_rph = 0;            // (t / kRing) & 1 of the S/dP stream
     int flushes = 0;
     auto issue_sdp = [&](int t) {
-      const int bh = (item0 + t) / tpb;
-      if (bh != s_bh) {
+      if (t == 0 || s_pos == 0) {
         tc::mbar_wait(smem_u32(&kv_full[s_kvn & 1]), (uint32_t)(s_kvn >> 1) & 1u);
-        s_bh = bh;
         ++s_kvn;
       }
-      const int kb = (s_kvn - 1) & 1, rs = t % kRing, g = t & 1;
+      if (++s_pos == tpb) s_pos = 0;
+      const int kb = (s_kvn - 1) & 1, rs = s_rs, g = t & 1;
+      const uint32_t rph = s_rph;
+      if (++s_rs == kRing) { s_rs = 0; s_rph ^= 1u; }
       TRACE(1, t, 0);
-      tc::mbar_wait(smem_u32(&ring_full[rs]), (uint32_t)(t / kRing) & 1u);
+      tc::mbar_wait(smem_u32(&ring_full[rs]), rph);
       TRACE(1, t, 1);
       tc::fence_after_sync();
       if (tc::elect_one()) {
@@ -188,12 +194,14 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_bwd_tc_kernel(const __grid_
     if (ntiles > 0) issue_sdp(0);
     if (ntiles > 1) issue_sdp(1);
     for (int t = 0; t < ntiles; ++t) {
-      const int bh = (item0 + t) / tpb, g = t & 1, rs = t % kRing;
-      const bool first_of_bh = bh != m_bh;
-      if (first_of_bh) { m_bh = bh; ++m_kvn; }
+      const int g = t & 1, rs = m_rs;
+      if (++m_rs == kRing) m_rs = 0;
+      const bool first_of_bh = t == 0 || m_pos == 0;
+      if (first_of_bh) ++m_kvn;
       const int kb = (m_kvn - 1) & 1;
       const bool last_tile = t + 1 == ntiles;
-      const bool last_of_bh = !last_tile && ((item0 + t + 1) / tpb != bh);
+      const bool last_of_bh = !last_tile && (m_pos == tpb - 1);
+      if (++m_pos == tpb) m_pos = 0;
       TRACE(1, t, 2);
       tc::mbar_wait(smem_u32(&ds_ready[g]), (uint32_t)(t >> 1) & 1u);
       TRACE(1, t, 3);
@@ -239,18 +247,16 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_bwd_tc_kernel(const __grid_
     const int L = p.L;
     const float sl2 = p.scale_log2, scale = p.scale;
     int flushes = 0;   // counted identically in both groups and the MMA warp
-    int cur_bh = -1;
+    int nb = b0, nh = h0, pos = rem0;   // (batch, head, tile-in-head) of tile t, advanced once per tile
     for (int t = 0; t < ntiles; ++t) {
-      const int item = item0 + t;
-      const int bh = item / tpb;
+      const int b = nb, h = nh;
       const bool last_tile = t + 1 == ntiles;
-      const bool flush = last_tile || ((item + 1) / tpb != bh);
+      const bool flush = last_tile || (pos == tpb - 1);
+      if (++pos == tpb) { pos = 0; if (++nh == p.H) { nh = 0; ++nb; } }
       if ((t & 1) != g) {            // the other group's tile: only keep the flush counter in step
         if (flush) ++flushes;
         continue;
       }
-      const int b = bh / p.H, h = bh - b * p.H;
-      (void)cur_bh;
       TRACE(2 + g, t, 0);
       tc::mbar_wait(smem_u32(&sdp_full[g]), (uint32_t)(t >> 1) & 1u);
       TRACE(2 + g, t, 1);
@@ -410,10 +416,8 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_bwd_tc_kernel(const __grid_
     }
   } else {
     // ===== warp 10: dQ TMA-store issuer =====
+    int b = b0, h = h0, tile = rem0;
     for (int t = 0; t < ntiles; ++t) {
-      const int item = item0 + t;
-      const int bh = item / tpb, tile = item - bh * tpb;
-      const int b = bh / p.H, h = bh - b * p.H;
       tc::mbar_wait(smem_u32(&dq_staged), (uint32_t)t & 1u);
       if (tc::elect_one()) {
         tc::tma_store_3d(&p.tmdQ, smem + kOffStage, h * kD, tile * kQT, b);
@@ -423,6 +427,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_bwd_tc_kernel(const __grid_
         if (t + 1 == ntiles) tc::tma_store_wait<0>();
       }
       __syncwarp();
+      if (++tile == tpb) { tile = 0; if (++h == p.H) { h = 0; ++b; } }
     }
   }
 

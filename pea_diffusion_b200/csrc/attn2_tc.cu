@@ -107,6 +107,11 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_fwd_tc_kernel(const __grid_
   const int item0 = blockIdx.x * p.tiles_per_cta;
   const int ntiles = min(p.tiles_per_cta, p.total_tiles - item0);
   const int tpb = p.tiles_per_bh;
+  // Work items are consecutive, so every role walks (batch, head, tile) with counters; the only integer divisions of the
+  // kernel are these.  (The MMA warp is a single latency-bound instruction stream that shares its scheduler with three
+  // softmax warps: four divisions per tile in it were a third of the tile period.)
+  const int bh0 = item0 / tpb, rem0 = item0 - bh0 * tpb;
+  const int b0 = bh0 / p.H, h0 = bh0 - b0 * p.H;
 
   if (warp == 0 && lane == 0) {
     tc::prefetch_tmap(&p.tmQ); tc::prefetch_tmap(&p.tmKV); tc::prefetch_tmap(&p.tmO);
@@ -140,12 +145,10 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_fwd_tc_kernel(const __grid_
 
   if (warp == 0) {
     // ===== TMA producer =====
-    int cur_bh = -1, kv_n = 0;
+    int kv_n = 0;
+    int b = b0, h = h0, tile = rem0;
     for (int t = 0; t < ntiles; ++t) {
-      const int item = item0 + t;
-      const int bh = item / tpb, tile = item - bh * tpb;
-      const int b = bh / p.H, h = bh - b * p.H;
-      if (bh != cur_bh) {   // new (batch, head): next K|V buffer (freed by the last P V that read it two loads ago)
+      if (t == 0 || tile == 0) {   // new (batch, head): next K|V buffer (freed by the last P V that read it two loads ago)
         const int kb = kv_n & 1;
         tc::mbar_wait(smem_u32(&kv_empty[kb]), ((uint32_t)(kv_n >> 1) & 1u) ^ 1u);
         if (tc::elect_one()) {
@@ -155,7 +158,6 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_fwd_tc_kernel(const __grid_
           tc::tma_load_3d(smem + kOffKV + kb * kKVBuf + kKVBytes, &p.tmKV, bk, p.C + h * kD, 0, b);
         }
         __syncwarp();
-        cur_bh = bh;
         ++kv_n;
       }
       const int s = t % kQStages;
@@ -167,6 +169,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_fwd_tc_kernel(const __grid_
         tc::tma_load_3d(smem + kOffQ + s * kQBytes, &p.tmQ, fb, h * kD, tile * kQT, b);
       }
       __syncwarp();
+      if (++tile == tpb) { tile = 0; if (++h == p.H) { h = 0; ++b; } }
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
@@ -174,16 +177,18 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_fwd_tc_kernel(const __grid_
     // MN-major tile (V as B of P V): [key][d], 16 keys per K step = 2048 B.
     constexpr uint64_t kDescK = ((uint64_t)1 << 16) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
     constexpr uint64_t kDescMN = ((uint64_t)(kKVBytes >> 4) << 16) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
-    int s_bh = -1, s_kvn = 0;       // K|V bookkeeping of the S stream (runs one tile ahead of the P V stream)
-    int o_bh = -1, o_kvn = 0;
+    int s_pos = rem0, s_kvn = 0;    // tile-in-head position and K|V bookkeeping of the S stream (runs ahead of the P V stream)
+    int o_pos = rem0, o_kvn = 0;
+    int s_j = 0;                    // t % kGroups of the S stream, as a counter
+    int o_j = 0; uint32_t o_ph = 0; // t % kGroups and (t / kGroups) & 1 of the P V stream
     auto issue_s = [&](int t) {
-      const int bh = (item0 + t) / tpb;
-      if (bh != s_bh) {
+      if (t == 0 || s_pos == 0) {   // first tile of a (batch, head) in this CTA's range
         tc::mbar_wait(smem_u32(&kv_full[s_kvn & 1]), (uint32_t)(s_kvn >> 1) & 1u);
-        s_bh = bh;
         ++s_kvn;
       }
-      const int kb = (s_kvn - 1) & 1, qs = t % kQStages, j = t % kGroups;
+      if (++s_pos == tpb) s_pos = 0;
+      const int kb = (s_kvn - 1) & 1, qs = t % kQStages, j = s_j;
+      if (++s_j == kGroups) s_j = 0;
       TRACE(1, t, 0);
       tc::mbar_wait(smem_u32(&q_full[qs]), (uint32_t)(t / kQStages) & 1u);
       TRACE(1, t, 1);
@@ -205,19 +210,27 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_fwd_tc_kernel(const __grid_
     if (ntiles > 0) issue_s(0);
     if (ntiles > 1) issue_s(1);
     for (int t = 0; t < ntiles; ++t) {
-      const int bh = (item0 + t) / tpb, j = t % kGroups;
+      const int j = o_j;
+      const uint32_t ph = o_ph;
+      if (++o_j == kGroups) { o_j = 0; o_ph ^= 1u; }
       // With one tile per (batch, head) -- three different heads in tiles t, t+1, t+2 -- the K|V buffer S(t+2) needs is the
       // one P V(t) still reads: its load waits for kv_empty, which P V(t) commits, so S(t+2) must then follow P V(t).
+      // (Tiles t+1 and t+2 can both open a new head only when every head has a single tile.)
       const bool s_ahead = t + 2 < ntiles;
-      const bool s_after = s_ahead && (item0 + t + 2) / tpb != (item0 + t + 1) / tpb && (item0 + t + 1) / tpb != bh;
+#ifdef PEA_FWD_S_AFTER
+      const bool s_after = s_ahead;
+#else
+      const bool s_after = s_ahead && tpb == 1;
+#endif
       if (s_ahead && !s_after) issue_s(t + 2);
-      if (bh != o_bh) { o_bh = bh; ++o_kvn; }
+      if (t == 0 || o_pos == 0) ++o_kvn;
       const int kb = (o_kvn - 1) & 1;
-      const bool last_of_bh = (t + 1 < ntiles) && ((item0 + t + 1) / tpb != bh);
+      const bool last_of_bh = (t + 1 < ntiles) && (o_pos == tpb - 1);
+      if (++o_pos == tpb) o_pos = 0;
       TRACE(1, t, 2);
-      tc::mbar_wait(smem_u32(&p_ready[j]), (uint32_t)(t / kGroups) & 1u);
+      tc::mbar_wait(smem_u32(&p_ready[j]), ph);
       TRACE(1, t, 3);
-      if (t >= kGroups) tc::mbar_wait(smem_u32(&tmem_free[j]), (uint32_t)(t / kGroups - 1) & 1u);  // O[j] of tile t-3 read out
+      if (t >= kGroups) tc::mbar_wait(smem_u32(&tmem_free[j]), ph ^ 1u);  // O[j] of tile t-3 read out
       tc::fence_after_sync();
       if (tc::elect_one()) {
         const uint32_t va = (smem + kOffKV + kb * kKVBuf + kKVBytes) >> 4;
@@ -241,11 +254,10 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_fwd_tc_kernel(const __grid_
     const bool issuer = threadIdx.x == 64 + g * 128;
     const int L = p.L;
     const float sl2 = p.scale_log2;
-    for (int t = g; t < ntiles; t += kGroups) {
-      const uint32_t ph = (uint32_t)(t / kGroups) & 1u;
-      const int item = item0 + t;
-      const int bh = item / tpb, tile = item - bh * tpb;
-      const int b = bh / p.H, h = bh - b * p.H;
+    int b = b0, h = h0, tile = rem0 + g;   // (batch, head, tile) of this group's current item, advanced kGroups at a time
+    uint32_t ph = 0;
+    for (int t = g; t < ntiles; t += kGroups, ph ^= 1u, tile += kGroups) {
+      while (tile >= tpb) { tile -= tpb; if (++h == p.H) { h = 0; ++b; } }
       TRACE(2 + g, t, 0);
       tc::mbar_wait(smem_u32(&s_full[g]), ph);
       TRACE(2 + g, t, 1);
