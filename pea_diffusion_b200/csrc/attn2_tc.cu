@@ -217,11 +217,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_fwd_tc_kernel(const __grid_
       // one P V(t) still reads: its load waits for kv_empty, which P V(t) commits, so S(t+2) must then follow P V(t).
       // (Tiles t+1 and t+2 can both open a new head only when every head has a single tile.)
       const bool s_ahead = t + 2 < ntiles;
-#ifdef PEA_FWD_S_AFTER
-      const bool s_after = s_ahead;
-#else
-      const bool s_after = s_ahead && tpb == 1;
-#endif
+      const bool s_after = s_ahead && tpb == 1;   // (always issuing S(t+2) after P V(t) measured 1.5 % slower)
       if (s_ahead && !s_after) issue_s(t + 2);
       if (t == 0 || o_pos == 0) ++o_kvn;
       const int kb = (o_kvn - 1) & 1;

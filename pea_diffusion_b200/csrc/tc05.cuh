@@ -22,18 +22,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-#ifdef PEA_WAIT_HINT
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-#else
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-#endif
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-#ifdef PEA_WAIT_HINT
-      : "r"(bar), "r"(parity), "r"((uint32_t)PEA_WAIT_HINT)
-#else
       : "r"(bar), "r"(parity)
-#endif
       : "memory");
   return ok != 0;
 }
