@@ -14,8 +14,8 @@
 //                  dV^T += dO^T P   SS  M64 N80 K128 -> dKV lanes  0-15 of each quarter   (A = dO, B = P, both MN-major)
 //                  dK^T += Q^T  dS  SS  M64 N80 K128 -> dKV lanes 16-31 of each quarter   (A = Q,  B = dS)
 //                dK / dV are formed TRANSPOSED (rows = head dim, columns = keys): an M64 MMA fetches 2 KB of A + 2.5 KB of B
-//                per K=16 step where the M128 "rows = 128 padded keys" form fetched 4 KB + 2 KB, and shared-memory operand
-//                fetch is what bounds this kernel.  An M64 accumulator occupies lanes 0-15 of the four 32-lane quarters,
+//                per K=16 step where the M128 "rows = 128 padded keys" form fetched 4 KB + 2 KB (42 vs 50 cycles per MMA in
+//                isolation, tools/mma_probe.cu; 4 % on the kernel).  An M64 accumulator occupies lanes 0-15 of the four 32-lane quarters,
 //                so the second one interleaves into lanes 16-31 of the same 80 columns.  They accumulate in TMEM across
 //                the CTA's consecutive tiles of one (batch, head).
 //   warps 2..5   softmax group 0 (even tiles), warps 6..9 group 1 (odd tiles); thread = query row = TMEM lane:

@@ -383,8 +383,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
 // ---------------------------------------------------------------------------------------------------------------------
 // CTA-pair variant (cta_group::2): a cluster of two CTAs on adjacent SMs computes one 256 x 256 tile.  Each CTA stages its
 // own 128 rows of A and its own 128-row half of the B tile; the leader's single thread issues M256 N256 K16 MMAs that read
-// both CTAs' shared memory, so every SM fetches only 8 KB of operands per 128-cycle MMA (64 B/clk -- the measured SS
-// operand-fetch rate) instead of 12 KB: the tensor pipe is no longer operand-starved (67 % -> ~95 % duty).
+// both CTAs' shared memory.  The single-CTA kernel is bound by shared-memory bandwidth -- every operand byte is written by
+// TMA and read by the MMA through the same 128 B/clk: 48 KB + 48 KB per 512 cycles of math = 192 B/clk -> 67 % duty, while
+// the MMA alone reaches 98 % (tools/mma_probe.cu) -- and the pair moves only 32 KB + 32 KB per SM for the same math.
 // Barrier protocol: TMA loads of BOTH CTAs credit the LEADER's full barrier; tcgen05.commit multicasts to the empty /
 // accumulator-full barriers of both CTAs; the peer's epilogue warps release the accumulator on the leader's barrier through
 // a shared::cluster arrive.  Single-plane operands only (the throughput mode).
