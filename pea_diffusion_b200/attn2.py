@@ -185,13 +185,16 @@ class Attn2Group:
                 getattr(a.to_v, "lora_layer", None) is None for a in self.attns)
         return self._supported
 
-    def project(self, context: Tensor, dtype):
+    def project(self, context: Tensor, dtype, layer: int = -1):
         """-> (kv_all [B*L, total], token or None) for the context tensor OBJECT the UNet passed down.  Recomputed when
         a different tensor (or an in-place modified one, a different dtype or grad mode) arrives; otherwise the
-        pass's -- or, for a denoise loop that keeps feeding the same tensor, the loop's -- projection is reused."""
+        pass's -- or, for a denoise loop that keeps feeding the same tensor, the loop's -- projection is reused.
+        Under autograd a call from the FIRST attn2 layer always starts a new pass (own projection node, own dK|dV
+        accumulator), even for the same tensor object: two passes must never share one gradient accumulator."""
         need_grad = torch.is_grad_enabled() and context.requires_grad
         key = (context._version, dtype, need_grad)
-        if self._ctx_ref is context and self._ctx_key == key and self._kv_all is not None:
+        new_pass = need_grad and layer == 0
+        if not new_pass and self._ctx_ref is context and self._ctx_key == key and self._kv_all is not None:
             tok, self._token = self._token, None     # only the first layer of a pass carries the token
             return self._kv_all, tok
         ctx = context.to(dtype)
@@ -279,8 +282,8 @@ class PEAAttn2Processor:
         if self.group is not None and id(attn) in self.group.index and self.group.supported(dt):
             # all layers' K|V from ONE projection GEMM per forward pass (and per denoise loop when the context is reused)
             B, L, _ = encoder_hidden_states.shape
-            kv_all, token = self.group.project(encoder_hidden_states, dt)
             i = self.group.index[id(attn)]
+            kv_all, token = self.group.project(encoder_hidden_states, dt, i)
             off, c2 = self.group.offsets[i], self.group.widths[i]
             kv = kv_all.view(B, L, self.group.total)[:, :, off:off + c2]
             o = _Attn2GroupedFn.apply(q, token, kv, self.group, i, attn.heads, float(attn.scale))

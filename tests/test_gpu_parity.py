@@ -532,6 +532,12 @@ def test_group_projection_matches_per_layer_path():
         out2 = unet(x, t, ctx2, added_cond_kwargs=kw)[0]
         (out * gout.float()).sum().backward()
         (out2 * gout.float()).sum().backward()
+        # ... and two passes over the SAME context tensor object: the second must not join the first one's accumulator
+        ctx3 = ctx.detach().clone().requires_grad_(True)
+        o3a = unet(x, t, ctx3, added_cond_kwargs=kw)[0]
+        o3b = unet(x, t, ctx3, added_cond_kwargs=kw)[0]
+        ((o3a + o3b) * gout.float()).sum().backward()
+        assert rel_err(o3a, out.detach()) < 1e-6 and rel_err(ctx3.grad.float(), 2 * ctx.grad.float()) < 1e-2
         res.append((torch.cat([out, out2]).detach().float(), torch.cat([ctx.grad, ctx2.grad]).float()))
         has_group = any(getattr(p, "group", None) is not None for p in procs.values())
         assert has_group == grouped
