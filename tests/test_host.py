@@ -153,3 +153,32 @@ def test_batch_stager_needs_cuda():
     from pea_diffusion_b200._lib import PeaError
     with pytest.raises(PeaError, match="no CPU fallback"):
         BatchStager("cpu")
+
+
+def test_attn2_group_layout_and_weight_cache_on_host_modules():
+    """Attn2Group bookkeeping needs no GPU: column slices in forward-call order, one concatenated [Wk; Wv] per weight
+    version, LoRA on any to_k / to_v sends the group back to the per-layer path."""
+    from pea_diffusion_b200.attn2 import Attn2Group
+
+    class A(torch.nn.Module):
+        def __init__(self, c, dc):
+            super().__init__()
+            self.to_k = torch.nn.Linear(dc, c, bias=False)
+            self.to_v = torch.nn.Linear(dc, c, bias=False)
+
+    torch.manual_seed(0)
+    attns = [A(64, 32), A(128, 32), A(64, 32)]
+    g = Attn2Group(attns)
+    assert g.widths == [128, 256, 128] and g.offsets == [0, 128, 384] and g.total == 512
+    assert [g.index[id(a)] for a in attns] == [0, 1, 2]
+    w = g.weights(torch.float32, torch.device("cpu"))
+    assert w.shape == (512, 32) and g.weights(torch.float32, torch.device("cpu")) is w          # cached
+    assert torch.equal(w[128:256], attns[1].to_k.weight) and torch.equal(w[256:384], attns[1].to_v.weight)
+    with torch.no_grad():
+        attns[2].to_v.weight.mul_(2.0)                                                           # version bump -> rebuilt
+    w2 = g.weights(torch.float32, torch.device("cpu"))
+    assert w2 is not w and torch.equal(w2[448:], attns[2].to_v.weight)
+    assert g.supported(torch.bfloat16)
+    attns[0].to_k.lora_layer = object()
+    g._supported = None
+    assert not g.supported(torch.bfloat16)
