@@ -73,7 +73,10 @@ int pea_kd_scale_grads(const pea_kd_tap* taps, int ntaps, int B, pea_dtype dtype
  *   q, o, dq, do : [B, N, H*d] rows of stride ld_q elements (head h occupies columns [h*d, (h+1)*d))
  *   k, v         : [B, L, H*d] rows of stride ld_kv elements, batch stride bs_kv elements (K|V may interleave)
  *   dk, dv       : fp32, same indexing as k, v with ld_dkv / bs_dkv; ACCUMULATED into (caller zero-fills)
- * L <= 80 (77 for CLIP; 52/64/32 for the other encoders), d in {64} (+{40,80,160}: see DESIGN.md).
+ * L <= 80 (77 for CLIP; 52/64/32 for the other encoders), d in {64} (+{40,48,80,160}: see DESIGN.md).
+ * Alignment: q / k / v / o / do / dq 16-byte aligned with ld_* and bs_kv multiples of 8 elements (128-bit row accesses,
+ * TMA boxes); dk / dv 8-byte aligned with even ld_dkv / bs_dkv.  d = 64 runs the tcgen05/TMA kernels, the other head
+ * sizes the warp-MMA kernels.  Violations return PEA_EINVAL with the reason in pea_last_error().
  * -------------------------------------------------------------------------------------------------------- */
 typedef struct {
   int B, N, L, H, d;
