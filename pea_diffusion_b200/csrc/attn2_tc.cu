@@ -7,19 +7,19 @@
 //
 // Persistent grid: one CTA per SM, each walking a CONTIGUOUS range of (batch, head, 128-row query tile) work items
 // (query tile fastest), so the Q ring never drains and K|V is reloaded only when (batch, head) changes (double
-// buffered, prefetched).  448 threads:
+// buffered, prefetched).  480 threads:
 //   warp 0      TMA producer: K|V tiles (rows >= L zero-filled by TMA), Q tiles into a 4-deep ring
-//   warp 1      TMEM allocator + MMA issuer, software pipelined  S(t+1) = Q K^T  ahead of  O(t) = P V:
-//                 S = Q K^T   tcgen05.mma SS, M128 N80 K64  -> TMEM S[t&1]
-//                 O = P [V|1] tcgen05.mma TS, M128 N80 K80  -> TMEM O[t&1]   (A = P straight from TMEM; the ones block
+//   warp 14     S issuer:    S = Q K^T   tcgen05.mma SS, M128 N80 K64  -> TMEM S[t % 3], up to three tiles ahead
+//   warp 1      TMEM allocator + P V issuer:
+//                 O = P [V|1] tcgen05.mma TS, M128 N80 K80  -> TMEM O[t % 3]  (A = P straight from TMEM; the ones block
 //                                                                          of B makes column 64 the row sum of P)
 //   warps 2..13 three softmax/epilogue groups of four warps, tiles dealt round-robin; thread = query row = TMEM lane:
 //               tcgen05.ld S, single-pass softmax (all keys are in the tile: no online rescaling and no cross-thread
 //               reduction), unnormalised P -> 16-bit -> tcgen05.st over S's own columns, later tcgen05.ld O, scale by
 //               1/rowsum, 128B-swizzled staging tile, TMA store (clips the N tail).
 // Per tile a group is mostly waiting on round trips (TMEM ld/st, MMA commits: ~3500 clk of latency for ~1000 clk of issue;
-// profiles/r1_attn2_fwd_timeline.txt), so three groups are in flight; S runs two tiles ahead of P V and the TMA engine up
-// to four Q tiles ahead.  TMEM: 480 of 512 columns (S/P x3, O x3).
+// profiles/r1_attn2_fwd_timeline.txt), so three groups are in flight; S runs up to three tiles ahead of P V and the TMA
+// engine up to four Q tiles ahead.  TMEM: 480 of 512 columns (S/P x3, O x3).
 // Algorithmic bytes per tile: 128 x 64 x 2 B in + the same out; FLOPs 4 x 128 x 80 x 64.
 #include "tc05.cuh"
 
@@ -31,7 +31,8 @@ constexpr int kD = 64;                   // head dim
 constexpr int kLP = 80;                  // padded key count
 constexpr int kQStages = 4;
 constexpr int kGroups = 3;                    // softmax / epilogue groups (4 warps each), tiles dealt round-robin
-constexpr int kThreads = 64 + kGroups * 128;
+constexpr int kSWarp = 2 + 4 * kGroups;       // the S = Q K^T issuer (warp 1 issues P V)
+constexpr int kThreads = 64 + kGroups * 128 + 32;
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kTmemS = 0, kTmemSStride = 80, kTmemO = 256, kTmemOStride = 80;   // 3 x 80 + 3 x 80 columns <= 512
 constexpr int kNO = kD + 16;                 // O accumulator width: 64 value columns + the row-sum column (16: N granularity)
@@ -172,53 +173,15 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_fwd_tc_kernel(const __grid_
       if (++tile == tpb) { tile = 0; if (++h == p.H) { h = 0; ++b; } }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    // K-major tiles (Q, K): 128-byte rows, 8-row groups 1024 B apart; K=16 step = 32 B inside the swizzle atom.
+    // ===== P V issuer =====
     // MN-major tile (V as B of P V): [key][d], 16 keys per K step = 2048 B.
-    constexpr uint64_t kDescK = ((uint64_t)1 << 16) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
     constexpr uint64_t kDescMN = ((uint64_t)(kKVBytes >> 4) << 16) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
-    int s_pos = rem0, s_kvn = 0;    // tile-in-head position and K|V bookkeeping of the S stream (runs ahead of the P V stream)
-    int o_pos = rem0, o_kvn = 0;
-    int s_j = 0;                    // t % kGroups of the S stream, as a counter
-    int o_j = 0; uint32_t o_ph = 0; // t % kGroups and (t / kGroups) & 1 of the P V stream
-    auto issue_s = [&](int t) {
-      if (t == 0 || s_pos == 0) {   // first tile of a (batch, head) in this CTA's range
-        tc::mbar_wait(smem_u32(&kv_full[s_kvn & 1]), (uint32_t)(s_kvn >> 1) & 1u);
-        ++s_kvn;
-      }
-      if (++s_pos == tpb) s_pos = 0;
-      const int kb = (s_kvn - 1) & 1, qs = t % kQStages, j = s_j;
-      if (++s_j == kGroups) s_j = 0;
-      TRACE(1, t, 0);
-      tc::mbar_wait(smem_u32(&q_full[qs]), (uint32_t)(t / kQStages) & 1u);
-      TRACE(1, t, 1);
-      // S/P[j] of tile t-2 need no barrier: P(t-2) was consumed by the P V MMA issued earlier by this same thread, and
-      // tcgen05.mma executes in issue order.  Only O[j] is guarded (below, before P V(t)).
-      tc::fence_after_sync();
-      if (tc::elect_one()) {
-        const uint32_t qa = (smem + kOffQ + qs * kQBytes) >> 4, ka = (smem + kOffKV + kb * kKVBuf) >> 4;
-#pragma unroll
-        for (int k = 0; k < kD / 16; ++k)
-          tc::mma_f16_ss(tmem + kTmemS + j * kTmemSStride, kDescK | (uint64_t)(qa + k * 2), kDescK | (uint64_t)(ka + k * 2), p.idesc_s, k > 0);
-        tc::mma_commit(smem_u32(&s_full[j]));
-        tc::mma_commit(smem_u32(&q_empty[qs]));
-      }
-      __syncwarp();
-    };
-    // S runs two tiles ahead of P V: S(t+2) reuses the S/P buffer of tile t-1, whose P V was issued one iteration ago
-    // (tcgen05.mma executes in issue order), so the softmax groups never wait for S.
-    if (ntiles > 0) issue_s(0);
-    if (ntiles > 1) issue_s(1);
+    int o_pos = rem0, o_kvn = 0;    // tile-in-head position and K|V bookkeeping of the P V stream
+    int o_j = 0; uint32_t o_ph = 0; // t % kGroups and (t / kGroups) & 1
     for (int t = 0; t < ntiles; ++t) {
       const int j = o_j;
       const uint32_t ph = o_ph;
       if (++o_j == kGroups) { o_j = 0; o_ph ^= 1u; }
-      // With one tile per (batch, head) -- three different heads in tiles t, t+1, t+2 -- the K|V buffer S(t+2) needs is the
-      // one P V(t) still reads: its load waits for kv_empty, which P V(t) commits, so S(t+2) must then follow P V(t).
-      // (Tiles t+1 and t+2 can both open a new head only when every head has a single tile.)
-      const bool s_ahead = t + 2 < ntiles;
-      const bool s_after = s_ahead && tpb == 1;   // (always issuing S(t+2) after P V(t) measured 1.5 % slower)
-      if (s_ahead && !s_after) issue_s(t + 2);
       if (t == 0 || o_pos == 0) ++o_kvn;
       const int kb = (o_kvn - 1) & 1;
       const bool last_of_bh = (t + 1 < ntiles) && (o_pos == tpb - 1);
@@ -238,7 +201,39 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_fwd_tc_kernel(const __grid_
         if (last_of_bh) tc::mma_commit(smem_u32(&kv_empty[kb]));   // K|V buffer reusable once these MMAs have read it
       }
       __syncwarp();
-      if (s_after) issue_s(t + 2);
+    }
+  } else if (warp == kSWarp) {
+    // ===== S issuer.  S and P V are issued by two warps: one latency-bound instruction stream issuing both (and sharing
+    // its scheduler with three softmax warps) paced the whole pipeline -- 18.4 -> 16.4 us at N = 1024, C = 1280.  Ordering
+    // with the P V warp is explicit: S(t) reuses S/P[t % 3], free once P V(t-3) has completed (o_full); a K|V buffer is
+    // released by the last P V of its head (kv_empty) and S of the head after next simply waits for the reload, so any
+    // number of tiles per head works without special cases. =====
+    // K-major tiles (Q, K): 128-byte rows, 8-row groups 1024 B apart; K=16 step = 32 B inside the swizzle atom.
+    constexpr uint64_t kDescK = ((uint64_t)1 << 16) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
+    int s_pos = rem0, s_kvn = 0, j = 0;
+    uint32_t jph = 0;
+    for (int t = 0; t < ntiles; ++t) {
+      if (t == 0 || s_pos == 0) {
+        tc::mbar_wait(smem_u32(&kv_full[s_kvn & 1]), (uint32_t)(s_kvn >> 1) & 1u);
+        ++s_kvn;
+      }
+      if (++s_pos == tpb) s_pos = 0;
+      const int kb = (s_kvn - 1) & 1, qs = t % kQStages;
+      TRACE(1, t, 0);
+      tc::mbar_wait(smem_u32(&q_full[qs]), (uint32_t)(t / kQStages) & 1u);
+      TRACE(1, t, 1);
+      if (t >= kGroups) tc::mbar_wait(smem_u32(&o_full[j]), jph ^ 1u);   // P V(t-3) done with P in S/P[j]
+      tc::fence_after_sync();
+      if (tc::elect_one()) {
+        const uint32_t qa = (smem + kOffQ + qs * kQBytes) >> 4, ka = (smem + kOffKV + kb * kKVBuf) >> 4;
+#pragma unroll
+        for (int k = 0; k < kD / 16; ++k)
+          tc::mma_f16_ss(tmem + kTmemS + j * kTmemSStride, kDescK | (uint64_t)(qa + k * 2), kDescK | (uint64_t)(ka + k * 2), p.idesc_s, k > 0);
+        tc::mma_commit(smem_u32(&s_full[j]));
+        tc::mma_commit(smem_u32(&q_empty[qs]));
+      }
+      __syncwarp();
+      if (++j == kGroups) { j = 0; jph ^= 1u; }
     }
   } else {
     // ===== softmax + epilogue groups: warp w owns TMEM lanes [32*(w%4), +32); thread = query row =====
