@@ -31,7 +31,7 @@ print(f"N={N} C={Cc}: cycles since kernel entry of CTA 0 (cold L2)")
 print("prologue done", ev(0, 0, 14) - t0)
 ntiles = (B * H * ((N + 127) // 128) + 147) // 148
 for t in range(min(ntiles, 12)):
-    g = t & 1
-    print(f"t{t:2d} g{g} prod issue {ev(0, t, 0) - t0:6d} | mma q_wait {ev(1, t, 0) - t0:6d} q_full {ev(1, t, 1) - t0:6d} p_wait {ev(1, t, 2) - t0:6d} p_ready {ev(1, t, 3) - t0:6d}"
+    g = t % 3   # three softmax groups, tiles dealt round-robin (roles 2, 3, 4 in the trace buffer)
+    print(f"t{t:2d} g{g} prod issue {ev(0, t, 0) - t0:6d} | S-warp q_wait {ev(1, t, 0) - t0:6d} q_full {ev(1, t, 1) - t0:6d} | PV-warp p_wait {ev(1, t, 2) - t0:6d} p_ready {ev(1, t, 3) - t0:6d}"
           f" | sm s_wait {ev(2 + g, t, 0) - t0:6d} s_full {ev(2 + g, t, 1) - t0:6d} p_arrive {ev(2 + g, t, 2) - t0:6d} o_wait {ev(2 + g, t, 3) - t0:6d} o_full {ev(2 + g, t, 4) - t0:6d} stored {ev(2 + g, t, 5) - t0:6d}")
-print("group done:", ev(2, 63, 6) - t0, ev(3, 63, 6) - t0)
+print("group done:", ev(2, 63, 6) - t0, ev(3, 63, 6) - t0, ev(4, 63, 6) - t0)
