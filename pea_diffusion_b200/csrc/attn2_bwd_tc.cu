@@ -443,11 +443,8 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_bwd_tc_kernel(const __grid_
 
 template <typename T>
 int launch_bwd_tc(const BwdParams& p, int ctas, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    PEA_CUDA(cudaFuncSetAttribute(attn2_bwd_tc_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-    attr_set = true;
-  }
+  static std::atomic<unsigned long long> attr_done{0};
+  if (int rc = ensure_dynamic_smem(attn2_bwd_tc_kernel<T>, (int)kSmemBytes, attr_done)) return rc;
   attn2_bwd_tc_kernel<T><<<ctas, kThreads, kSmemBytes, st>>>(p);
   PEA_LAUNCH_CHECK();
   return PEA_OK;

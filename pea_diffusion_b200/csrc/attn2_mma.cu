@@ -351,8 +351,8 @@ template <int D> constexpr size_t bwd_smem() { return (size_t)(2 * kLP + 3 * kWa
 
 template <typename T, int D>
 int launch_fwd(const AttnParams& p, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) { PEA_CUDA(cudaFuncSetAttribute(attn2_fwd_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem<D>())); attr_set = true; }
+  static std::atomic<unsigned long long> attr_done{0};
+  if (int rc = ensure_dynamic_smem(attn2_fwd_kernel<T, D>, (int)fwd_smem<D>(), attr_done)) return rc;
   dim3 grid((p.N + kWarps * 16 - 1) / (kWarps * 16), p.H, p.B);
   attn2_fwd_kernel<T, D><<<grid, kWarps * 32, fwd_smem<D>(), st>>>(p);
   PEA_LAUNCH_CHECK();
@@ -360,8 +360,8 @@ int launch_fwd(const AttnParams& p, cudaStream_t st) {
 }
 template <typename T, int D>
 int launch_bwd(const AttnParams& p, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) { PEA_CUDA(cudaFuncSetAttribute(attn2_bwd_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_smem<D>())); attr_set = true; }
+  static std::atomic<unsigned long long> attr_done{0};
+  if (int rc = ensure_dynamic_smem(attn2_bwd_kernel<T, D>, (int)bwd_smem<D>(), attr_done)) return rc;
   dim3 grid((p.N + p.rows_per_cta - 1) / p.rows_per_cta, p.H, p.B);
   attn2_bwd_kernel<T, D><<<grid, kWarps * 32, bwd_smem<D>(), st>>>(p);
   PEA_LAUNCH_CHECK();

@@ -48,6 +48,21 @@ inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_
 inline size_t dtype_size(pea_dtype t) { return t == PEA_F32 ? 4 : 2; }
 int num_sms();
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device).  The attribute belongs to the device's copy
+// of the function, and although the design is one process per GPU nothing here should break when one process drives
+// several: `done` is a per-kernel bit mask indexed by device ordinal.
+template <typename Kernel>
+inline int ensure_dynamic_smem(Kernel kernel, int bytes, std::atomic<unsigned long long>& done) {
+  int dev = 0;
+  PEA_CUDA(cudaGetDevice(&dev));
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (!(done.load(std::memory_order_acquire) & bit)) {
+    PEA_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    done.fetch_or(bit, std::memory_order_release);
+  }
+  return PEA_OK;
+}
+
 // ---- device helpers ------------------------------------------------------------------------------------------
 template <typename T> struct VecTraits;
 

@@ -522,11 +522,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc2_kernel(const __grid_cons
 
 template <int SA, int SB, int A_MN, int B_MN, int BN>
 int launch(const GemmParams& p, int ctas, size_t smem, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    PEA_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<SA, SB, A_MN, B_MN, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemBudget + 1024)));
-    attr_set = true;
-  }
+  static std::atomic<unsigned long long> attr_done{0};
+  if (int rc = ensure_dynamic_smem(gemm_tc_kernel<SA, SB, A_MN, B_MN, BN>, (int)(kSmemBudget + 1024), attr_done)) return rc;
   gemm_tc_kernel<SA, SB, A_MN, B_MN, BN><<<ctas, kThreads, smem, st>>>(p);
   PEA_LAUNCH_CHECK();
   return PEA_OK;
@@ -544,11 +541,8 @@ int dispatch_major(const GemmParams& p, int ctas, size_t smem, cudaStream_t st) 
 
 template <int A_MN, int B_MN>
 int launch_pair(const GemmParams& p, int pairs, size_t smem, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    PEA_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemBudget + 1024)));
-    attr_set = true;
-  }
+  static std::atomic<unsigned long long> attr_done{0};
+  if (int rc = ensure_dynamic_smem(gemm_tc2_kernel<A_MN, B_MN>, (int)(kSmemBudget + 1024), attr_done)) return rc;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(2 * pairs);
   cfg.blockDim = dim3(kThreads);
