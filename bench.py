@@ -11,10 +11,19 @@ to the adapter through the student (dQ / dContext only), adapter-grad all-reduce
 Workload (config.workload): BASELINE.json configs[1] -- random-init SDXL-shaped UNet shell x2, 1024 px (128x128 latent),
 bf16, batch 8 per GPU, 77x1024 CLIP-shaped embeddings -> shipped 6.03 M adapter; synthetic data.
 
-One JSON line on stdout (rank 0).  `value` = samples/s with inputs resident in HBM; `e2e` = the same with pinned-host
-inputs copied H2D and the loss read back D2H inside every timed step; `roofline` = the fused attn2 forward+backward
-kernels' algorithmic bytes / CUDA-event time over the timed region against MEASURED_PEAKS.json; `cpu_baseline` = the
-oracle (CPU restatement of the reference path) timed on this box's host cores on a bounded sample.
+One JSON line on stdout (rank 0):
+  value          samples/s with inputs resident in HBM (weak scaling: batch 8 per GPU)
+  e2e            the same with pinned-host inputs copied H2D and the loss read back D2H inside every timed step
+  roofline       the fused attn2 forward+backward kernels: algorithmic bytes / CUDA-event time of
+                 every launch inside a replayed CUDA graph of the step, against MEASURED_PEAKS.json; plus
+                 .per_kernel        every kernel family of the library inside the step
+                 .in_step_marginal  bracket-free: (replayed step) - (the same step captured without the attention launches)
+                 .sweep             BASELINE.json configs[3]: the config-4 attn2 sweep (B=8; N 1024/4096/16384; C 640/1280;
+                                    L 77, and 52 / 64 once), each launch alone, L2 flushed -- metric M2
+  strong         configs[2]: the same step at GLOBAL batch 64 (64/W per rank, micro-batches of 8), samples/s
+  infer          configs[4]: 30 forward-only UNet calls, fp16, UNet batch 8, constant context (K|V cache), vs stock processors
+  dp_params_identical   bitwise equality of the adapter on every rank after the timed steps
+  cpu_baseline   the oracle (CPU restatement of the reference path) timed on this box's host cores on a bounded sample
 """
 from __future__ import annotations
 
@@ -43,13 +52,19 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
-    ap.add_argument("--batch", type=int, default=8, help="per-GPU batch (config 2: 8)")
+    ap.add_argument("--batch", type=int, default=8, help="per-GPU (micro-)batch (config 2: 8)")
+    ap.add_argument("--global-batch", type=int, default=64, help="config 3's fixed global batch for the strong-scaling sub-run (0: skip it)")
     ap.add_argument("--latent", type=int, default=128, help="latent side (128 = 1024 px)")
-    ap.add_argument("--adapter-precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16"], help="UNet / activation dtype (fp16 = the reference's --precision 16, with loss scaling)")
+    ap.add_argument("--adapter-precision", default=None, choices=["bf16", "fp16", "fp32"])
+    ap.add_argument("--comm-dtype", default="fp32", choices=["fp32", "bf16"], help="payload of the adapter-gradient all-reduce")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager step instead of the CUDA-graph replay")
+    ap.add_argument("--no-capture-comm", action="store_true", help="keep the NCCL all-reduce outside the CUDA graph")
     ap.add_argument("--overlap-teacher", type=int, default=1, help="1: teacher forward on its own stream, concurrent with the student forward (0: in line)")
-    ap.add_argument("--timed-only", action="store_true", help="skip the eager per-kernel pass and the e2e loop (ncu launch-list runs)")
+    ap.add_argument("--timed-only", action="store_true", help="only the timed region (ncu launch-list runs)")
+    ap.add_argument("--no-sweep", action="store_true")
+    ap.add_argument("--no-infer", action="store_true")
     ap.add_argument("--tiny", action="store_true", help="tiny shell (debug only; the JSON line says so)")
     return ap.parse_args()
 
@@ -61,8 +76,20 @@ def peaks():
         return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
 
 
+def workload_config(args, world):
+    """The `config` object: identical for both arms (`--impl b200` and `--impl reference`)."""
+    latent = 16 if args.tiny else args.latent
+    return {"workload": ("TINY DEBUG SHELL -- not the benchmark config" if args.tiny else
+                         f"train_sdxl_zh.py KD step, random-init SDXL UNet shell x2 (student+teacher), {8 * latent}px "
+                         f"({latent}x{latent} latent), batch {args.batch}/GPU, 77x1024 embeddings -> 6.03M adapter, teacher+student "
+                         "forward, backward to the adapter, AdamW"),
+            "global_batch": world * args.batch, "parallelism": f"dp{world}",
+            "l2": "no explicit flush in the step: every step streams 10.3 GB of weights plus activations (>> 126 MB L2); "
+                  "roofline.sweep flushes L2 between iterations"}
+
+
 # ------------------------------------------------------------------------------------------------- synthetic data
-def synth_batch(B, latent, cfg, in_dim, seed, pinned=False):
+def synth_batch(B, latent, cfg, in_dim, seed):
     """seeded N(0,1) latents/noise/embeddings, zh = [0,1]*, 10 % CFG mask."""
     g = torch.Generator().manual_seed(seed)
     r = lambda *s: torch.randn(*s, generator=g)
@@ -96,75 +123,6 @@ def host_stage(batch, act_dtype):
 
 def to_device(hbatch, dev):
     return {k: v.to(dev, non_blocking=True) for k, v in hbatch.items()}
-
-
-def profile_in_graph(trainer, adapter, replays):
-    """Capture trainer._forward_backward into a fresh CUDA graph with ops.TIMER in external-event mode, replay it
-    ``replays`` times and return ({kernel: {launches, ms, bytes, flops}} summed over the replays, graph keep-alive)."""
-    import torch
-    from pea_diffusion_b200 import ops
-    params = list(adapter.parameters())
-    saved = [q.grad for q in params]                    # the trainer's own graph writes into these: keep them attached
-    for q in params:
-        q.grad = None
-    side = torch.cuda.Stream()
-    side.wait_stream(torch.cuda.current_stream())
-    total = {}
-    g = torch.cuda.CUDAGraph()
-    try:
-        ops.TIMER.reset(True, external=True)
-        with torch.cuda.graph(g, stream=side):
-            trainer._forward_backward(trainer._static_in)
-        ops.TIMER.enabled = False
-        for _ in range(replays):
-            g.replay()
-            torch.cuda.synchronize()
-            for name, r in ops.TIMER.summary().items():
-                t = total.setdefault(name, {"launches": 0, "ms": 0.0, "bytes": 0, "flops": 0})
-                for k in t:
-                    t[k] += r[k]
-    finally:
-        ops.TIMER.reset(False)
-        for q, g_ in zip(params, saved):
-            q.grad = g_
-    return total, g
-
-
-def event_pair_overhead_us(dev, in_graph, n=100):
-    """Median elapsed time of a CUDA-event pair around the library's smallest launch (pea_cfg_select on 8 elements),
-    taken the same way as the per-kernel figures (event-record nodes inside a replayed CUDA graph, or eager): what the
-    bracketing itself adds to every per-launch time (record + launch latency + a ~2 us minimal kernel).  Reported next to
-    the raw roofline numbers; never subtracted from `achieved` / `frac`."""
-    import torch
-    from pea_diffusion_b200 import ops
-    m = torch.zeros(1, dtype=torch.uint8, device=dev)
-    a = torch.zeros(1, 8, dtype=torch.bfloat16, device=dev)
-    out = ops.cfg_select(m, a, a)   # warm-up (and the output buffer the captured launches reuse)
-    pairs = []
-
-    def body():
-        for _ in range(n):
-            e0 = torch.cuda.Event(enable_timing=True, external=in_graph)
-            e1 = torch.cuda.Event(enable_timing=True, external=in_graph)
-            e0.record()
-            ops.cfg_select(m, a, a)
-            e1.record()
-            pairs.append((e0, e1))
-
-    if in_graph:
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g, stream=side):
-            body()
-        g.replay()
-        g.replay()
-    else:
-        body()
-    torch.cuda.synchronize()
-    t = sorted(e0.elapsed_time(e1) for e0, e1 in pairs)
-    del out
-    return t[len(t) // 2] * 1e3
 
 
 # ------------------------------------------------------------------------------------------------- clocks
@@ -209,7 +167,7 @@ class ClockSampler:
 def cpu_reference_sample(steps: int, warmup: int, latent: int, batch: int, tiny: bool = False):
     """The reference's algorithm for the path (oracle/pea_oracle.py: stock attention processors, PyTorch adapter and
     loss, autograd INCLUDING the discarded UNet weight gradients, as the reference runs it) on the host cores.
-    Returns (seconds per step, description)."""
+    Imports nothing that binds libpea_b200.so.  Returns (seconds per step, cores)."""
     from oracle import pea_oracle as O
     from pea_diffusion_b200.shell.unet import UNet2DConditionShell, UNetConfig
     cores = os.cpu_count() or 1
@@ -237,29 +195,48 @@ def cpu_reference_sample(steps: int, warmup: int, latent: int, batch: int, tiny:
     return sum(times) / len(times), cores
 
 
+def native_libs_mapped():
+    """Names of this repo's shared objects mapped into the current process (the reference arm must list none)."""
+    try:
+        return sorted({ln.split()[-1] for ln in open("/proc/self/maps") if ROOT in ln and ln.rstrip().endswith(".so")})
+    except Exception:
+        return []
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    latent, batch = (16, 2) if args.tiny else (32, 1)
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    if args.tiny:
+        latent, batch = 16, 2
+        probe = None
+    else:
+        # bounded sample: one sample at a 64x64 latent (a quarter of the benchmark's tokens) when the whole --steps/--warmup
+        # run then fits in ~4 minutes on this box's cores, else a 32x32 latent; decided from one timed 32x32 step
+        sec32, _ = cpu_reference_sample(1, 1, 32, 1)
+        probe = sec32
+        latent, batch = (64, 1) if sec32 * 6.0 * (args.steps + args.warmup) <= 240.0 else (32, 1)
     sec, cores = cpu_reference_sample(args.steps, args.warmup, latent, batch, args.tiny)
     # scale to the metric's unit: a 1024-px sample has (128/latent)^2 times the latent tokens of the timed sample
-    scale = (args.latent / latent) ** 2
+    full = 16 if args.tiny else args.latent
+    scale = (full / latent) ** 2
     value = batch / sec / scale
     sample = (f"oracle KD step (student fwd+bwd incl. discarded UNet weight grads, teacher fwd, PyTorch adapter+loss, AdamW), "
-              f"fp32, SDXL shell, batch {batch}, {latent}x{latent} latent; samples/s divided by {scale:.0f} (token ratio to "
-              f"{args.latent}x{args.latent}) -- linear-in-tokens scaling flatters the CPU (self-attention is quadratic)")
+              f"fp32, SDXL shell, batch {batch}, {latent}x{latent} latent, {sec:.2f} s/step; samples/s divided by {scale:.0f} (token "
+              f"ratio to {full}x{full}: an EXTRAPOLATION that flatters the CPU, self-attention being quadratic in tokens)" +
+              (f"; 32x32 probe step {probe:.2f} s" if probe is not None else ""))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "fp32", "data": "synthetic",
-            "config": {"workload": "train_sdxl_zh.py KD step, random-init SDXL UNet shell x2, 1024px, batch 8/GPU (timed on a bounded CPU sample)",
-                       "l2": "working set >> L2"},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
-            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            "dtype": "fp32", "data": "synthetic", "config": workload_config(args, world),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                             "note": "one host process whatever --gpus says: the CPU arm does not scale with N"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "native_libs_mapped": native_libs_mapped()}
     emit(line)
 
 
-# ------------------------------------------------------------------------------------------------- our arm
+# ------------------------------------------------------------------------------------------------- our arm: helpers
 _REAL_STDOUT = None
 
 
@@ -279,6 +256,226 @@ def emit(line: dict) -> None:
     out.flush()
 
 
+def capture_fb(trainer, timer_external=False):
+    """Capture trainer's forward+backward (no collectives) into a fresh CUDA graph -> (graph, library launches captured)."""
+    from pea_diffusion_b200 import _lib, ops
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    g = torch.cuda.CUDAGraph()
+    world, trainer.reducer.world = trainer.reducer.world, 1      # measurement graphs carry no NCCL nodes
+    n0 = _lib.launch_count()
+    try:
+        if timer_external:
+            ops.TIMER.reset(True, external=True)
+        with torch.cuda.graph(g, stream=side):
+            trainer._forward_backward(trainer._static_in)
+    finally:
+        ops.TIMER.enabled = False
+        trainer.reducer.world = world
+    return g, _lib.launch_count() - n0
+
+
+def profile_in_graph(trainer, replays):
+    """Per-launch CUDA-event times INSIDE a replayed graph of the step (event-record nodes around every library launch).
+    -> ({kernel: {launches, ms, bytes, flops}} summed over the replays, launches per step, graph keep-alive)."""
+    from pea_diffusion_b200 import ops
+    total = {}
+    try:
+        g, nlaunch = capture_fb(trainer, timer_external=True)
+        for _ in range(replays):
+            g.replay()
+            torch.cuda.synchronize()
+            for name, r in ops.TIMER.summary().items():
+                t = total.setdefault(name, {"launches": 0, "ms": 0.0, "bytes": 0, "flops": 0})
+                for k in t:
+                    t[k] += r[k]
+    finally:
+        ops.TIMER.reset(False)
+    return total, nlaunch, g
+
+
+def time_replays(g, n):
+    for _ in range(2):
+        g.replay()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(n):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); g.replay(); e1.record(); e1.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def in_step_marginal(trainer, replays=5):
+    """Bracket-free cost of the attention launches inside the step: median replay time of the captured forward+backward
+    minus the same graph captured with ops.SKIP_ATTN2 (outputs allocated, nothing launched).  Serial schedule (no teacher
+    overlap) in both, so the difference is the device time the 210 launches occupy, launch gaps included."""
+    from pea_diffusion_b200 import ops
+    g, _ = capture_fb(trainer)
+    t_full = time_replays(g, replays)
+    del g
+    torch.cuda.empty_cache()
+    ops.SKIP_ATTN2 = True
+    try:
+        g, _ = capture_fb(trainer)
+    finally:
+        ops.SKIP_ATTN2 = False
+    t_skip = time_replays(g, replays)
+    del g
+    return t_full, t_skip
+
+
+def event_pair_overhead_us(dev, n=100):
+    """Median elapsed time of an event-record-node pair around the library's smallest launch inside a replayed graph: what
+    the bracketing itself adds to every per-launch figure.  Reported beside the raw numbers; never subtracted from `frac`."""
+    from pea_diffusion_b200 import ops
+    m = torch.zeros(1, dtype=torch.uint8, device=dev)
+    a = torch.zeros(1, 8, dtype=torch.bfloat16, device=dev)
+    out = ops.cfg_select(m, a, a)
+    pairs = []
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=side):
+        for _ in range(n):
+            e0 = torch.cuda.Event(enable_timing=True, external=True)
+            e1 = torch.cuda.Event(enable_timing=True, external=True)
+            e0.record()
+            ops.cfg_select(m, a, a)
+            e1.record()
+            pairs.append((e0, e1))
+    g.replay(); g.replay()
+    torch.cuda.synchronize()
+    t = sorted(e0.elapsed_time(e1) for e0, e1 in pairs)
+    del out
+    return t[len(t) // 2] * 1e3
+
+
+def timed_isolated(fn, iters, scratch, warm=5):
+    """Median CUDA-event time (us) of `fn` launched alone: L2 flushed by reading a 256 MB scratch (leaves clean lines), the
+    host kept ahead of the device by a short spin kernel so no launch latency lands between the events."""
+    for _ in range(warm):
+        fn()
+    ts = []
+    for _ in range(iters):
+        scratch.sum()
+        torch.cuda._sleep(400000)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record()
+        e1.synchronize()
+        ts.append(e0.elapsed_time(e1) * 1e3)
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def attn2_sweep(dev, hbm_gbs, iters=20, dtype=torch.bfloat16):
+    """BASELINE.json configs[3] / SURVEY.md section 8d config 4 (metric M2)."""
+    from pea_diffusion_b200 import ops
+    scratch = torch.empty(64 << 20, device=dev, dtype=torch.int32)
+    rows = []
+    B = 8
+    for (C, H) in ((640, 10), (1280, 20)):
+        for N in (1024, 4096, 16384):
+            for L in ((77, 64, 52) if (N == 4096 and C == 640) else (77,)):
+                q = torch.randn(B, N, C, device=dev, dtype=dtype)
+                kv = torch.randn(B, L, 2 * C, device=dev, dtype=dtype)
+                do = torch.randn(B, N, C, device=dev, dtype=dtype)
+                dkv = torch.zeros(B, L, 2 * C, device=dev, dtype=torch.float32)
+                d = C // H
+                fb, bb = ops.attn2_bytes(B, N, L, C, 2)
+                tf = timed_isolated(lambda: ops.attn2_fwd(q, kv, H, d ** -0.5), iters, scratch)
+                tb = timed_isolated(lambda: ops.attn2_bwd(q, kv, do, H, d ** -0.5, dkv=dkv), iters, scratch)
+                rows.append({"B": B, "N": N, "C": C, "H": H, "L": L, "fwd_us": round(tf, 2), "bwd_us": round(tb, 2),
+                             "fwd_frac": round(fb / tf / 1e3 / hbm_gbs, 4), "bwd_frac": round(bb / tb / 1e3 / hbm_gbs, 4),
+                             "fwdbwd_frac": round((fb + bb) / (tf + tb) / 1e3 / hbm_gbs, 4),
+                             "fwd_TFLOPs": round(4 * B * N * L * C / tf / 1e6, 1), "bwd_TFLOPs": round(10 * B * N * L * C / tb / 1e6, 1)})
+                del q, kv, do, dkv
+    return rows
+
+
+def gemm_sweep(dev, iters=20, dtype=torch.bfloat16):
+    """The GEMM shapes the path launches (adapter chain at M = 2*8*77 rows, the all-layer K|V projection, the all-layer
+    dContext) with cuBLAS timed beside each on the same operands -- context for the tensor-pipe figures."""
+    from pea_diffusion_b200 import ops
+    scratch = torch.empty(64 << 20, device=dev, dtype=torch.int32)
+    shapes = [("adapter_fwd_1024x1024", 1232, 1024, 1024, True, 0), ("adapter_fwd_1280x1024", 1232, 1280, 1024, True, 0),
+              ("adapter_fwd_fc_2048x1280", 1232, 2048, 1280, True, 0), ("adapter_dx_1024x1024", 1232, 1024, 1024, False, 0),
+              ("adapter_dw_1024x1024", 1024, 1024, 1232, None, 0),
+              ("kvproj_all_layers", 616, 166400, 2048, True, 0), ("dctx_all_layers", 616, 2048, 166400, False, 1)]
+    rows = []
+    for name, M, N, K, bk, splitk in shapes:
+        if bk is None:        # dW = G^T X: both operands stored [rows = K, *]
+            A = torch.randn(K, M, device=dev, dtype=dtype); Bm = torch.randn(K, N, device=dev, dtype=dtype)
+            o = torch.empty(M, N, device=dev, dtype=torch.float32)
+            fn = lambda: ops.gemm([A], [Bm], M, N, K, a_kmajor=False, b_kmajor=False, out0=o)
+            lib = lambda: torch.matmul(A.t(), Bm)
+        else:
+            A = torch.randn(M, K, device=dev, dtype=dtype)
+            Bm = torch.randn(N, K, device=dev, dtype=dtype) if bk else torch.randn(K, N, device=dev, dtype=dtype)
+            if splitk:
+                o = torch.zeros(M, N, device=dev, dtype=torch.float32)
+                kb, tiles = (K + 63) // 64, ((M + 127) // 128) * ((N + 127) // 128)
+                split = max(1, min(kb // 8, (4 * 148 + tiles - 1) // tiles))
+                fn = lambda: ops.gemm([A], [Bm], M, N, K, b_kmajor=bk, out0=o, accumulate=True, split_k=split)
+            else:
+                o = torch.empty(M, N, device=dev, dtype=dtype)
+                fn = lambda: ops.gemm([A], [Bm], M, N, K, b_kmajor=bk, out0=o)
+            lib = (lambda: torch.matmul(A, Bm.t())) if bk else (lambda: torch.matmul(A, Bm))
+        t = timed_isolated(fn, iters, scratch)
+        tl = timed_isolated(lib, iters, scratch)
+        rows.append({"name": name, "M": M, "N": N, "K": K, "us": round(t, 2), "TFLOPs": round(2 * M * N * K / t / 1e6, 1),
+                     "cublas_us": round(tl, 2), "cublas_TFLOPs": round(2 * M * N * K / tl / 1e6, 1)})
+        del A, Bm, o
+    return rows
+
+
+def infer_subrun(dev, steps=30):
+    """BASELINE.json configs[4] (tests/test_sdxl_zh.py:299-406): SDXL shell fp16, UNet batch 8 (4 prompts x CFG), `steps`
+    forward-only calls with a constant context; scheduler math replaced by `latents -= 0.01 * eps` (out of scope).
+    Fused processors with the loop-invariant K|V cache vs the stock processors on the same weights."""
+    from pea_diffusion_b200 import _lib, attn2
+    from pea_diffusion_b200.shell.unet import StockAttnProcessor, UNet2DConditionShell, UNetConfig
+    cfg = UNetConfig.sdxl()
+    torch.manual_seed(0)
+    with torch.device(dev):
+        unet = UNet2DConditionShell(cfg)
+    unet = unet.half().requires_grad_(False)
+    g = torch.Generator(device=dev).manual_seed(1)
+    ctx = torch.randn(8, 77, 2048, device=dev, dtype=torch.float16, generator=g)
+    kw = {"text_embeds": torch.randn(8, 1280, device=dev, dtype=torch.float16, generator=g),
+          "time_ids": torch.tensor([[1024.0, 1024, 0, 0, 1024, 1024]] * 8, device=dev)}
+    lat0 = torch.randn(8, 4, 128, 128, device=dev, dtype=torch.float16, generator=g)
+    tsteps = [torch.tensor([999 - 33 * i], device=dev) for i in range(steps)]
+    res, outs = {}, {}
+    for arm in ("stock", "fused"):
+        unet.set_attn_processor(StockAttnProcessor())
+        if arm == "fused":
+            attn2.install(unet, cache_kv=True)
+
+        def loop():
+            lat = lat0.clone()
+            with torch.no_grad():
+                for i in range(steps):
+                    lat = lat - 0.01 * unet(lat, tsteps[i], ctx, added_cond_kwargs=kw)[0]
+            return lat
+
+        loop()
+        torch.cuda.synchronize()
+        n0 = _lib.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); outs[arm] = loop(); e1.record()
+        torch.cuda.synchronize()
+        res[arm] = {"ms_per_unet_call": e0.elapsed_time(e1) / steps, "images_per_s": 4 / (e0.elapsed_time(e1) * 1e-3),
+                    "library_launches": _lib.launch_count() - n0}
+    ref = outs["stock"].float()
+    res["rel_err_vs_stock_after_%d_steps" % steps] = float((outs["fused"].float() - ref).norm() / ref.norm())
+    res["workload"] = f"SDXL shell fp16, UNet batch 8, {steps} forward-only calls, constant [8,77,2048] context, eager launches"
+    del unet
+    return res
+
+
+# ------------------------------------------------------------------------------------------------- our arm
 def main():
     args = parse()
     _guard_stdout()
@@ -298,24 +495,32 @@ def main():
 
     from pea_diffusion_b200 import _lib, adapter as A, attn2, ops
     from pea_diffusion_b200.shell.unet import UNet2DConditionShell, UNetConfig
-    from pea_diffusion_b200.train import KDTrainer
+    from pea_diffusion_b200.train import KDTrainer, parameter_checksums
     import copy
 
-    act = torch.bfloat16
+    act = torch.bfloat16 if args.dtype == "bf16" else torch.float16
+    ad_prec = args.adapter_precision or args.dtype
     cfg = UNetConfig.tiny("sdxl") if args.tiny else UNetConfig.sdxl()
     in_dim, hidden = (64, 64) if args.tiny else (1024, 1024)
     latent = 16 if args.tiny else args.latent
     pooled = cfg.projection_class_embeddings_input_dim - 6 * cfg.addition_time_embed_dim
-    torch.manual_seed(0)  # identical weights on every rank
+    torch.manual_seed(0)  # identical frozen weights on every rank (the adapter is broadcast from rank 0 by KDTrainer anyway)
     with torch.device(dev):
         student = UNet2DConditionShell(cfg)
     student = student.to(act)
     teacher = copy.deepcopy(student)
     attn2.install(student, freeze=True)
     attn2.install(teacher, freeze=True)
-    adapter = A.MLP(in_dim, pooled, hidden, cfg.cross_attention_dim, False, precision=args.adapter_precision).to(dev)
-    trainer = KDTrainer(student, teacher, adapter, "sdxl", lr=1e-5, cuda_graph=not args.no_graph, overlap_teacher=bool(args.overlap_teacher))
+    torch.manual_seed(rank)   # deliberately DIFFERENT adapter init per rank: the trainer's broadcast has to make them equal
+    adapter = A.MLP(in_dim, pooled, hidden, cfg.cross_attention_dim, False, precision=ad_prec).to(dev)
+    graph_mode = not args.no_graph
 
+    def make_trainer(overlap):
+        return KDTrainer(student, teacher, adapter, "sdxl", lr=1e-5, cuda_graph=graph_mode, overlap_teacher=overlap,
+                         comm_dtype=torch.bfloat16 if args.comm_dtype == "bf16" else None, capture_comm=not args.no_capture_comm,
+                         loss_scale=65536.0 if args.dtype == "fp16" else None, dynamic_loss_scale=args.dtype == "fp16")
+
+    trainer = make_trainer(bool(args.overlap_teacher))
     B = args.batch
     hbatch = host_stage(synth_batch(B, latent, cfg, in_dim, 1234 + rank), act)
     dbatch = to_device(hbatch, dev)
@@ -338,82 +543,41 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms) / steps
 
-    try:
-        for _ in range(max(args.warmup, 3)):
-            trainer.step(dbatch)
-        torch.cuda.synchronize()
-    except Exception as exc:
-        if not args.overlap_teacher:
-            raise
-        # the two-stream schedule is an optimisation, not part of the result: fall back to the in-line teacher forward
-        sys.stderr.write("bench: teacher/student stream overlap failed (%s); re-running without it\n" % str(exc).splitlines()[0][:200])
-        args.overlap_teacher = 0
-        trainer.close()
-        for q in adapter.parameters():
-            q.grad = None
-        trainer = KDTrainer(student, teacher, adapter, "sdxl", lr=1e-5, cuda_graph=not args.no_graph, overlap_teacher=False)
-        for _ in range(max(args.warmup, 3)):
-            trainer.step(dbatch)
-        torch.cuda.synchronize()
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
+        trainer.step(dbatch)
+    torch.cuda.synchronize()
 
     # ---- value: inputs resident in HBM ------------------------------------------------------------------------
     clocks = ClockSampler(local) if rank == 0 else None
-    graph_mode = not args.no_graph
-    n0 = _lib.launch_count()
     ops.TIMER.reset(not graph_mode)
+    n0 = _lib.launch_count()
     torch.cuda.nvtx.range_push("pea_timed")
     ms_step = timed(lambda: trainer.step(dbatch), args.steps)
     torch.cuda.nvtx.range_pop()
     ops.TIMER.enabled = False
-    launches = _lib.launch_count() - n0
-    prof_steps = args.steps
-    if graph_mode and not args.timed_only:
-        # A graph replay re-launches the kernels the capture recorded (launch_count only sees the capture), and CUDA
-        # events cannot bracket nodes inside a graph: run the SAME step eagerly for the per-kernel roofline figures and
-        # for the launch count.
-        prof_steps = min(args.steps, 3)
-        overlap_stream, trainer.teacher_stream = trainer.teacher_stream, None   # per-kernel times: one kernel at a time
-        n0 = _lib.launch_count()
-        ops.TIMER.reset(True)
-        torch.cuda.nvtx.range_push("pea_profiled_eager")
-        params = list(adapter.parameters())
-        static_grads = [q.grad for q in params]          # the graph writes into these tensors: keep them attached
-        for _ in range(prof_steps):
-            for q in params:
-                q.grad = None
-            trainer._forward_backward(dbatch)
-        torch.cuda.synchronize()
-        for q, g_ in zip(params, static_grads):
-            q.grad = g_
-        torch.cuda.nvtx.range_pop()
-        ops.TIMER.enabled = False
-        launches = (_lib.launch_count() - n0) * args.steps // prof_steps
-    ksum = ops.TIMER.summary()
+    launches_per_step = (_lib.launch_count() - n0) / args.steps   # eager mode; a graph replay re-launches what the capture recorded
+    ksum, prof_steps = ops.TIMER.summary(), args.steps
     ops.TIMER.reset(False)
-    timing_note = ("CUDA events around every launch of %d eager steps run right after the graph-replayed timed region"
-                   % prof_steps) if graph_mode else "CUDA events around every launch inside the timed steps"
+    timing_note = "CUDA events around every launch inside the timed eager steps"
+    marginal, ev_overhead_us = None, None
     if graph_mode and not args.timed_only:
-        # Per-kernel times INSIDE a replayed step: capture the same forward+backward once more with external events
-        # (event-record nodes) around every launch of the library, replay it, read the events after each replay.  The
-        # eager figures above carry ~5-10 us of host launch latency per bracket; these do not.
+        # Per-kernel times INSIDE a replayed step: the same forward+backward captured once more with event-record nodes
+        # around every library launch; serial schedule (no teacher/student overlap) so each kernel has the GPU to itself.
+        overlap_stream, trainer.teacher_stream = trainer.teacher_stream, None
         try:
-            g_steps = min(args.steps, 5)
-            ksum_g, _keep = profile_in_graph(trainer, adapter, g_steps)
-            if ksum_g.get("attn2_fwd", {}).get("launches", 0) > 0:
-                ksum, prof_steps = ksum_g, g_steps
-                timing_note = ("CUDA events recorded as event-record nodes around every launch inside %d replays of a CUDA graph of "
-                               "the same forward+backward, captured and replayed right after the timed region" % g_steps) + \
-                              ("; captured WITHOUT the teacher/student stream overlap of the timed region, so that each kernel has the GPU "
-                               "to itself while it is timed" if args.overlap_teacher else "")
+            prof_steps = min(args.steps, 5)
+            ksum, launches_per_step, _keep = profile_in_graph(trainer, prof_steps)
             del _keep
-        except Exception as exc:  # keep the eager figures; say why
-            timing_note += " (in-graph event timing failed: %s)" % (str(exc).splitlines()[0][:160] if str(exc) else type(exc).__name__)
-        trainer.teacher_stream = overlap_stream
+            timing_note = ("CUDA events recorded as event-record nodes around every library launch inside %d replays of a CUDA graph "
+                           "of the step's forward+backward (captured after the timed region, serial schedule: no teacher/student overlap, "
+                           "no collectives), so the brackets include the node-to-node launch latency" % prof_steps)
+            t_full, t_skip = in_step_marginal(trainer)
+            marginal = (t_full, t_skip)
+            ev_overhead_us = event_pair_overhead_us(dev)
+        finally:
+            trainer.teacher_stream = overlap_stream
         torch.cuda.empty_cache()
-    try:
-        ev_overhead_us = event_pair_overhead_us(dev, in_graph=timing_note.startswith("CUDA events recorded as event-record nodes"))
-    except Exception:
-        ev_overhead_us = None
 
     # ---- e2e: pinned host inputs -> H2D every step, loss read back D2H every step -------------------------------
     host_loss = torch.empty(4, dtype=torch.float32).pin_memory()
@@ -427,9 +591,24 @@ def main():
     else:
         e2e_step()
         ms_e2e = timed(e2e_step, args.steps)
-    clk = clocks.stop() if clocks else None
     h2d = sum(v.numel() * v.element_size() for v in hbatch.values())
 
+    # ---- strong scaling (configs[2]): global batch 64 -> 64/W per rank in micro-batches of `--batch` ------------------
+    strong = None
+    if args.global_batch and not args.timed_only and args.global_batch % (world * B) == 0:
+        micro = args.global_batch // (world * B)
+        s_steps = max(2, min(args.steps, 3))
+        trainer.step_accumulate([dbatch] * micro)
+        ms_strong = timed(lambda: trainer.step_accumulate([dbatch] * micro), s_steps)
+        strong = {"global_batch": args.global_batch, "per_rank_batch": micro * B, "micro_batches_per_step": micro, "steps": s_steps,
+                  "ms_per_step": ms_strong, "value": args.global_batch / (ms_strong * 1e-3), "unit": UNIT, "scaling": "strong",
+                  "note": "one optimizer step per global batch; gradients of the micro-batches accumulated on the device"}
+    clk = clocks.stop() if clocks else None
+    same, sums = parameter_checksums(adapter)
+    loss_now = [float(v) for v in trainer.step(dbatch).float().cpu()]
+
+    if world > 1:
+        dist.barrier()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -439,53 +618,88 @@ def main():
     at = {k: ksum.get(k, {"launches": 0, "ms": 0.0, "bytes": 0, "flops": 0}) for k in ("attn2_fwd", "attn2_bwd", "kd_mse", "gemm")}
     a_ms = at["attn2_fwd"]["ms"] + at["attn2_bwd"]["ms"]
     a_bytes = at["attn2_fwd"]["bytes"] + at["attn2_bwd"]["bytes"]
+    a_launch = at["attn2_fwd"]["launches"] + at["attn2_bwd"]["launches"]
     achieved = a_bytes / (a_ms * 1e-3) / 1e9 if a_ms > 0 else 0.0
     # DRAM traffic per launch (read + write) of the same launch mix, from the committed ncu --set full capture of the two
-    # shapes a step launches (profiles/r1_attn2_traffic.json); null on other workloads
+    # shapes a step launches; null on other workloads
     traffic, traffic_src = None, None
-    try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_attn2_traffic.json")))
-        if not args.tiny and args.latent == 128 and args.batch == 8:
-            traffic, traffic_src = tj["traffic_bytes_per_launch_step_mix"], "profiles/r1_attn2_traffic.json (bytes per launch, step mix; algorithmic: %d)" % tj["algorithmic_bytes_per_launch_step_mix"]
-    except Exception:
-        pass
+    for cand in ("r2_attn2_traffic.json", "r1_attn2_traffic.json"):
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", cand)))
+            if not args.tiny and args.latent == 128 and args.batch == 8:
+                traffic = tj["traffic_bytes_per_launch_step_mix"]
+                traffic_src = "profiles/%s (ncu --set full, bytes per launch, step mix; algorithmic: %d)" % (cand, tj["algorithmic_bytes_per_launch_step_mix"])
+            break
+        except Exception:
+            continue
     per_kernel = {k: {"launches_per_step": v["launches"] / prof_steps, "ms_per_step": v["ms"] / prof_steps,
+                      "us_per_launch": (v["ms"] * 1e3 / v["launches"] if v["launches"] else None),
                       "GBps": (v["bytes"] / (v["ms"] * 1e-3) / 1e9 if v["ms"] > 0 else 0.0),
                       "TFLOPs": (v["flops"] / (v["ms"] * 1e-3) / 1e12 if v["ms"] > 0 else 0.0)} for k, v in at.items()}
+    roof = {"bound": "hbm", "kernel": "attn2 fused forward + backward (all 70 layers x student fwd/bwd + teacher fwd)",
+            "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
+            "frac_of_nominal_8TBps": achieved / 8000.0,
+            "traffic": traffic, "traffic_source": traffic_src, "peak_source": pk_kind,
+            "algorithmic_bytes_per_step": a_bytes / prof_steps if prof_steps else None,
+            "bytes_formula": "SURVEY.md 8d: fwd 2BNCe + 2BLCe; bwd 3BNCe + 4BLCe (e = 2)",
+            "event_pair_overhead_us": ev_overhead_us, "timing": timing_note, "per_kernel": per_kernel}
+    if marginal is not None and a_launch:
+        t_full, t_skip = marginal
+        m_ms = t_full - t_skip
+        roof["in_step_marginal"] = {
+            "ms_step_with": t_full, "ms_step_without_attn2": t_skip, "attn2_ms_per_step": m_ms,
+            "us_per_launch": m_ms * 1e3 / (a_launch / prof_steps),
+            "GBps": (a_bytes / prof_steps) / (m_ms * 1e-3) / 1e9 if m_ms > 0 else None,
+            "frac": (a_bytes / prof_steps) / (m_ms * 1e-3) / 1e9 / pk["hbm_gbs"] if m_ms > 0 else None,
+            "how": "median replay time of the captured forward+backward minus the same capture with the attention launches "
+                   "removed (ops.SKIP_ATTN2): no event brackets, launch gaps included, inputs L2-resident as in training"}
     value = world * B / (ms_step * 1e-3)
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
-        "data": "synthetic",
-        "config": {"workload": ("TINY DEBUG SHELL -- not the benchmark config" if args.tiny else
-                                "train_sdxl_zh.py KD step, random-init SDXL UNet shell x2 (student+teacher), 1024px "
-                                f"({latent}x{latent} latent), bf16, batch {B}/GPU, teacher+student forward, backward to the 6.03M adapter, AdamW"),
-                   "global_batch": world * B, "parallelism": f"dp{world}", "adapter_precision": args.adapter_precision,
-                   "step_execution": ("CUDA graph replay (fwd+bwd captured once) + eager all-reduce/AdamW" if graph_mode else "eager") +
-                                     ("; teacher forward on a parallel stream / graph branch" if args.overlap_teacher else ""),
-                   "l2": "no explicit flush: every step streams 10.3 GB of weights plus activations (>> 126 MB L2)"},
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype,
+        "data": "synthetic", "config": workload_config(args, world),
+        "execution": {"adapter_precision": ad_prec, "comm_dtype": args.comm_dtype,
+                      "step": ("ONE CUDA graph per step: forward + backward" + (" + bucketed NCCL all-reduce (captured)" if world > 1 and not args.no_capture_comm else "") +
+                               ", then the fused AdamW launch" if graph_mode else "eager") +
+                              ("; teacher forward on a parallel graph branch" if args.overlap_teacher else "")},
         "e2e": {"value": world * B / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 16,
                 "ms_per_step": ms_e2e},
-        "gpu_launches": launches,
+        "gpu_launches": int(round(launches_per_step * args.steps)),
         "clocks": clk,
-        "roofline": {"bound": "hbm", "kernel": "attn2 fused forward + backward (all 70 layers x student fwd/bwd + teacher fwd)",
-                     "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
-                     "traffic": traffic, "traffic_source": traffic_src, "peak_source": pk_kind,
-                     "event_pair_overhead_us": ev_overhead_us,
-                     "frac_net_of_event_overhead": (a_bytes / (max(a_ms - ev_overhead_us * 1e-3 * (at["attn2_fwd"]["launches"] + at["attn2_bwd"]["launches"]), 1e-9) * 1e-3) / 1e9 / pk["hbm_gbs"]) if (a_ms > 0 and ev_overhead_us is not None) else None,
-                     "timing": timing_note,
-                     "per_kernel": per_kernel},
+        "roofline": roof,
+        "strong": strong,
+        "dp_params_identical": bool(same), "dp_param_checksums": sums, "loss": loss_now,
     }
-    if not args.no_cpu_baseline and world == 1:
-        try:
-            cl, cb = (16, 2) if args.tiny else (32, 1)
-            sec, cores = cpu_reference_sample(2, 1, cl, cb, args.tiny)
-            scale = (latent / cl) ** 2
-            line["cpu_baseline"] = {"value": cb / sec / scale, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"oracle KD step fp32, SDXL shell, batch {cb}, {cl}x{cl} latent, {sec:.2f} s/step; samples/s "
-                                              f"divided by {scale:.0f} (token ratio to {latent}x{latent})"}
-        except Exception as e:  # the GPU numbers stand on their own
-            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
+    if world == 1 and not args.timed_only:
+        # free the training state before the isolated-kernel sweeps
+        trainer.close()
+        del trainer, student, teacher
+        torch.cuda.empty_cache()
+        if not args.no_sweep and not args.tiny:
+            clocks2 = ClockSampler(local)
+            try:
+                roof["sweep"] = attn2_sweep(dev, pk["hbm_gbs"])
+                roof["sweep_gemm"] = gemm_sweep(dev)
+                roof["sweep_how"] = ("each launch alone, 5 warm-up + 20 timed iterations, CUDA events on the launching stream, L2 flushed by "
+                                     "reading 256 MB between iterations; median; fractions of the measured HBM peak")
+            except Exception as exc:
+                roof["sweep_error"] = str(exc).splitlines()[0][:200]
+            roof["sweep_clocks"] = clocks2.stop()
+        if not args.no_infer and not args.tiny:
+            try:
+                line["infer"] = infer_subrun(dev)
+            except Exception as exc:
+                line["infer"] = {"error": str(exc).splitlines()[0][:200]}
+        if not args.no_cpu_baseline:
+            try:
+                cl, cb = (16, 2) if args.tiny else (32, 1)
+                sec, cores = cpu_reference_sample(2, 1, cl, cb, args.tiny)
+                scale = (latent / cl) ** 2
+                line["cpu_baseline"] = {"value": cb / sec / scale, "unit": UNIT, "cores": cores, "kind": "port",
+                                        "sample": f"oracle KD step fp32, SDXL shell, batch {cb}, {cl}x{cl} latent, {sec:.2f} s/step; samples/s "
+                                                  f"divided by {scale:.0f} (token ratio to {latent}x{latent}; extrapolation)"}
+            except Exception as e:  # the GPU numbers stand on their own
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
     emit(line)
     if world > 1:
         dist.destroy_process_group()

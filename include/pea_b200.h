@@ -61,10 +61,13 @@ typedef struct {
 size_t pea_kd_workspace_bytes(const pea_kd_tap* taps, int ntaps, int B);
 int pea_kd_mse_fwd_bwd(const pea_kd_tap* taps, int ntaps, int B, pea_dtype dtype, float feature_weight,
                        float grad_scale, int skip_nonfinite, void* d_workspace, float* d_out, void* stream);
-/* Backward fix-up: d_grad *= (*d_upstream) * counted_flag; exits immediately on device when the factor is 1.
- * Needed only when autograd's upstream gradient is not the `grad_scale` assumed by the fused pass. */
+/* Backward fix-up: d_grad *= (*d_upstream) * inv_prescale * counted_flag; exits immediately on device when the factor
+ * is 1.  `inv_prescale` = 1 / the `grad_scale` the fused pass was given.  Under fp16 loss scaling (the reference trains
+ * with --precision 16 + DeepSpeed's loss scaler, train_sdxl_zh.sh:89) the caller passes its loss scale as `grad_scale`
+ * so that the gradient is scaled BEFORE it is rounded to fp16 (unscaled feature-KD coefficients, ~1e-8, flush to
+ * zero in fp16); autograd's upstream gradient then equals the loss scale and this pass has nothing to do. */
 int pea_kd_scale_grads(const pea_kd_tap* taps, int ntaps, int B, pea_dtype dtype, const float* d_upstream,
-                       const float* d_out, void* stream);
+                       float inv_prescale, const float* d_out, void* stream);
 
 /* ----------------------------------------------------------------------------------------------------------
  * attn2 core: softmax(q k^T * scale) v per head, keys resident in shared memory.

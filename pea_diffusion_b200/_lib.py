@@ -79,7 +79,7 @@ SYMBOLS = {
     "pea_kd_workspace_bytes": (C.c_size_t, [C.POINTER(KdTap), C.c_int, C.c_int]),
     "pea_kd_mse_fwd_bwd": (C.c_int, [C.POINTER(KdTap), C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int,
                                      C.c_void_p, C.c_void_p, C.c_void_p]),
-    "pea_kd_scale_grads": (C.c_int, [C.POINTER(KdTap), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pea_kd_scale_grads": (C.c_int, [C.POINTER(KdTap), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]),
     "pea_attn2_fwd": (C.c_int, [C.POINTER(Attn2Desc), C.c_void_p]),
     "pea_attn2_bwd": (C.c_int, [C.POINTER(Attn2Desc), C.c_void_p]),
     "pea_gemm": (C.c_int, [C.POINTER(GemmDesc), C.c_void_p]),
@@ -123,10 +123,20 @@ def stream_ptr(device: Optional[torch.device] = None) -> int:
 
 
 def require_cuda(*tensors: torch.Tensor) -> None:
+    """Every operand on the CURRENT CUDA device: the C side sizes grids, sets function attributes and launches on the
+    process's current device (one process per GPU), so a tensor on another device would run on a foreign stream."""
+    cur = None
     for t in tensors:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise PeaError("pea_diffusion_b200 kernels need CUDA tensors (there is no CPU fallback); got a "
                            f"{t.device} tensor of shape {tuple(t.shape)}")
+        if cur is None:
+            cur = torch.cuda.current_device()
+        if t.device.index != cur:
+            raise PeaError(f"tensor on {t.device} but the current CUDA device is cuda:{cur}; one process per GPU -- call "
+                           "torch.cuda.set_device(...) (or wrap the call in torch.cuda.device(...)) first")
 
 
 def ptr(t: Optional[torch.Tensor]) -> Optional[int]:

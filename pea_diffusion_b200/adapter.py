@@ -51,7 +51,7 @@ class _AdapterFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, nsplit: int, plane_dt: torch.dtype, n_chain: int, head: bool, pooled: bool, residual: bool,
-                x: Tensor, ln_w: Tensor, ln_b: Tensor, *wb: Optional[Tensor]):
+                x: Tensor, ln_w: Tensor, ln_b: Tensor, sink, *wb: Optional[Tensor]):
         ops.require_cuda(x, ln_w, ln_b)
         B, L, Din = x.shape
         M = B * L
@@ -94,13 +94,16 @@ class _AdapterFn(torch.autograd.Function):
         else:
             outs.append(xlast.to(x.dtype).view(B, L, -1))
         ctx.cfg = (nsplit, plane_dt, n_chain, head, pooled, residual, B, L)
-        ctx.saved = (x2d, mean, rstd, inputs, preacts, w_planes, ln_w, Ws, bs)
+        ctx.saved = (x2d, mean, rstd, inputs, preacts, w_planes, ln_w, ln_b, Ws, bs)
+        ctx.sink = sink
         return tuple(outs)
 
     @staticmethod
     def backward(ctx, *gouts: Optional[Tensor]):
         nsplit, plane_dt, n_chain, head, pooled, residual, B, L = ctx.cfg
-        x2d, mean, rstd, inputs, preacts, w_planes, ln_w, Ws, bs = ctx.saved
+        x2d, mean, rstd, inputs, preacts, w_planes, ln_w, ln_b, Ws, bs = ctx.saved
+        sink = ctx.sink     # optional gradient sink (train.GradAllReducer): dW / db are written straight into its flat
+        #                     communication buffer and the bucket's all-reduce starts while the rest of this backward runs
         M = B * L
         dev = x2d.device
         f32 = torch.float32
@@ -115,17 +118,26 @@ class _AdapterFn(torch.autograd.Function):
         def weight_grads(i: int, g_planes: Sequence[Tensor], g_full: Optional[Tensor]):
             W = Ws[i]
             if W.requires_grad:
-                dW = torch.empty(W.shape, device=dev, dtype=W.dtype)
+                slot = sink.slot(W) if sink is not None else None
+                dW = slot if slot is not None else torch.empty(W.shape, device=dev, dtype=W.dtype)
                 # dW[o, k] = sum_r g[r, o] h[r, k]: both operands are stored [rows, *] -> MN-major
                 ops.gemm(g_planes, inputs[i], W.shape[0], W.shape[1], M, a_kmajor=False, b_kmajor=False, out0=dW)
-                dWs[i] = dW
+                if slot is None:
+                    dWs[i] = dW
+                else:
+                    sink.mark_ready(W)
             if bs[i] is not None and bs[i].requires_grad:
                 db = torch.zeros(W.shape[0], device=dev, dtype=f32)
                 ops.colsum_accum(g_full if g_full is not None else g_planes[0], db)
                 if g_full is None:
                     for extra in g_planes[1:]:
                         ops.colsum_accum(extra, db)
-                dbs[i] = db.to(bs[i].dtype)
+                slot = sink.slot(bs[i]) if sink is not None else None
+                if slot is None:
+                    dbs[i] = db.to(bs[i].dtype)
+                else:
+                    slot.copy_(db)
+                    sink.mark_ready(bs[i])
 
         # ---- gradient w.r.t. the last chain pre-activation x -------------------------------------------------
         if head:
@@ -173,7 +185,16 @@ class _AdapterFn(torch.autograd.Function):
         flat: List[Optional[Tensor]] = []
         for i in range(n_lin):
             flat += [dWs[i], dbs[i]]
-        return (None, None, None, None, None, None, dx if want_dx else None, dgamma.to(ln_w.dtype), dbeta.to(ln_w.dtype), *flat)
+        g_lnw, g_lnb = dgamma.to(ln_w.dtype), dbeta.to(ln_w.dtype)
+        if sink is not None:
+            for prm, g in ((ln_w, g_lnw), (ln_b, g_lnb)):
+                slot = sink.slot(prm)
+                if slot is not None:
+                    slot.copy_(g)
+                    sink.mark_ready(prm)
+            g_lnw = None if sink.slot(ln_w) is not None else g_lnw
+            g_lnb = None if sink.slot(ln_b) is not None else g_lnb
+        return (None, None, None, None, None, None, dx if want_dx else None, g_lnw, g_lnb, None, *flat)
 
 
 def _run(module: nn.Module, x: Tensor, chain: Sequence[nn.Linear], head: Optional[nn.Linear], pooled: bool, residual: bool):
@@ -187,7 +208,7 @@ def _run(module: nn.Module, x: Tensor, chain: Sequence[nn.Linear], head: Optiona
     for lin in list(chain) + ([head] if head is not None else []):
         wb += [lin.weight, lin.bias]
     return _AdapterFn.apply(nsplit, plane_dt, len(chain), head is not None, pooled, residual, x, module.layernorm.weight,
-                            module.layernorm.bias, *wb)
+                            module.layernorm.bias, getattr(module, "_grad_sink", None), *wb)
 
 
 class MLP(nn.Module):

@@ -93,7 +93,9 @@ class _ProjectAllFn(torch.autograd.Function):
             raise RuntimeError(f"attn2 group: dContext requested after {state.bwd_calls} of {state.fwd_calls} layer "
                                "backwards -- the first attn2 layer is not upstream of all others in this network")
         wcat = group.weights(ctx_.dtype, state.dkv_all.device)
-        dkv16 = ops.split_planes(state.dkv_all.view(B * L, group.total), 1, ctx_.dtype)
+        # two 16-bit planes (hi + residual) of the fp32 accumulators, exactly as the per-layer path does: rounding the sum
+        # over all layers' query tiles to ONE bf16 plane before the dContext GEMM costs ~3 decimal digits for nothing
+        dkv16 = ops.split_planes(state.dkv_all.view(B * L, group.total), group.dctx_planes, ctx_.dtype)
         dctx = torch.zeros(B * L, Dc, device=wcat.device, dtype=torch.float32)
         kb = (group.total + 63) // 64
         tiles = ((B * L + 127) // 128) * ((Dc + 127) // 128)
@@ -162,7 +164,9 @@ class Attn2Group:
         self._token: Optional[Tensor] = None
         self._supported: Optional[bool] = None
         self.state: Optional[_PassState] = None
-        self.sms = torch.cuda.get_device_properties(0).multi_processor_count if torch.cuda.is_available() else 148
+        self.dctx_planes = 2                       # operand planes of dK|dV in the dContext GEMM (1 = throughput mode)
+        self.sms = (torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+                    if torch.cuda.is_available() else 148)
 
     def weights(self, dtype, device) -> Tensor:
         key = (dtype, device, tuple(a.to_k.weight._version for a in self.attns), tuple(a.to_v.weight._version for a in self.attns),
@@ -180,7 +184,8 @@ class Attn2Group:
         first layer's call; the answer is cached until the next projection)."""
         if self._supported is None:
             dc = self.attns[0].to_k.weight.shape[1]
-            self._supported = dc % 8 == 0 and all(
+            trainable = torch.is_grad_enabled() and any(a.to_k.weight.requires_grad or a.to_v.weight.requires_grad for a in self.attns)
+            self._supported = dc % 8 == 0 and not trainable and all(
                 a.to_k.weight.shape[1] == dc and getattr(a.to_k, "lora_layer", None) is None and
                 getattr(a.to_v, "lora_layer", None) is None for a in self.attns)
         return self._supported
@@ -192,7 +197,8 @@ class Attn2Group:
         Under autograd a call from the FIRST attn2 layer always starts a new pass (own projection node, own dK|dV
         accumulator), even for the same tensor object: two passes must never share one gradient accumulator."""
         need_grad = torch.is_grad_enabled() and context.requires_grad
-        key = (context._version, dtype, need_grad)
+        self.weights(dtype, context.device)          # refreshes _wkey: a weight update between passes invalidates cached K|V
+        key = (context._version, dtype, need_grad, self._wkey)
         new_pass = need_grad and layer == 0
         if not new_pass and self._ctx_ref is context and self._ctx_key == key and self._kv_all is not None:
             tok, self._token = self._token, None     # only the first layer of a pass carries the token
@@ -256,6 +262,8 @@ class PEAAttn2Processor:
             return False
         if getattr(attn.to_k, "lora_layer", None) is not None or getattr(attn.to_v, "lora_layer", None) is not None:
             return False
+        if torch.is_grad_enabled() and (attn.to_k.weight.requires_grad or attn.to_v.weight.requires_grad):
+            return False   # the fused path never forms dWk / dWv (frozen-UNet contract): trainable projections -> stock processor
         if getattr(attn, "norm_cross", None) or getattr(attn, "group_norm", None) is not None or \
                 getattr(attn, "spatial_norm", None) is not None or getattr(attn, "residual_connection", False) or \
                 getattr(attn, "rescale_output_factor", 1.0) != 1.0:
@@ -267,6 +275,8 @@ class PEAAttn2Processor:
 
     def __call__(self, attn, hidden_states: Tensor, encoder_hidden_states: Optional[Tensor] = None,
                  attention_mask: Optional[Tensor] = None, temb: Optional[Tensor] = None, scale: float = 1.0) -> Tensor:
+        if encoder_hidden_states is not None:
+            ops.require_cuda(hidden_states, encoder_hidden_states)     # cross-attention on host tensors: no CPU path, ever
         if not self._supported(attn, hidden_states, encoder_hidden_states, attention_mask):
             if encoder_hidden_states is not None and hidden_states.is_cuda and not PEAAttn2Processor._warned:
                 PEAAttn2Processor._warned = True   # never silent: a cross-attention call is leaving the fused kernels
@@ -276,7 +286,6 @@ class PEAAttn2Processor:
                 raise ops._lib.PeaError("PEAAttn2Processor: call outside the fused kernel's contract and no fallback processor set")
             return self.fallback(attn, hidden_states, encoder_hidden_states=encoder_hidden_states,
                                  attention_mask=attention_mask, temb=temb, scale=scale)
-        ops.require_cuda(hidden_states, encoder_hidden_states)
         dt = hidden_states.dtype
         q = attn.to_q(hidden_states)
         if self.group is not None and id(attn) in self.group.index and self.group.supported(dt):

@@ -424,7 +424,9 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_bwd_tc_kernel(const __grid_
         tc::tma_store_commit();
         tc::tma_store_wait_read<0>();
         tc::mbar_arrive(smem_u32(&stage_free));
-        if (t + 1 == ntiles) tc::tma_store_wait<0>();
+#ifndef PEA_EXP_WAITREAD
+        if (t + 1 == ntiles) tc::tma_store_wait<0>();   // (the global writes complete by grid end in any case)
+#endif
       }
       __syncwarp();
       if (++tile == tpb) { tile = 0; if (++h == p.H) { h = 0; ++b; } }

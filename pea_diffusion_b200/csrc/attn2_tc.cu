@@ -114,6 +114,21 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_fwd_tc_kernel(const __grid_
   const int bh0 = item0 / tpb, rem0 = item0 - bh0 * tpb;
   const int b0 = bh0 / p.H, h0 = bh0 - b0 * p.H;
 
+#ifdef PEA_EXP_PARINIT
+  if (warp == 0) {
+    // one barrier per lane: kv_full[2] kv_empty[2] | s_full, p_ready, o_full, tmem_free [kGroups each] | q_full, q_empty [kQStages each]
+    if (lane < 3) tc::prefetch_tmap(lane == 0 ? (const void*)&p.tmQ : lane == 1 ? (const void*)&p.tmKV : (const void*)&p.tmO);
+    if (lane < 2) tc::mbar_init(smem_u32(&kv_full[lane]), 1);
+    else if (lane < 4) tc::mbar_init(smem_u32(&kv_empty[lane - 2]), 1);
+    else if (lane < 4 + kGroups) tc::mbar_init(smem_u32(&s_full[lane - 4]), 1);
+    else if (lane < 4 + 2 * kGroups) tc::mbar_init(smem_u32(&p_ready[lane - 4 - kGroups]), 4);
+    else if (lane < 4 + 3 * kGroups) tc::mbar_init(smem_u32(&o_full[lane - 4 - 2 * kGroups]), 1);
+    else if (lane < 4 + 4 * kGroups) tc::mbar_init(smem_u32(&tmem_free[lane - 4 - 3 * kGroups]), 4);
+    else if (lane < 4 + 4 * kGroups + kQStages) tc::mbar_init(smem_u32(&q_full[lane - 4 - 4 * kGroups]), 1);
+    else if (lane < 4 + 4 * kGroups + 2 * kQStages) tc::mbar_init(smem_u32(&q_empty[lane - 4 - 4 * kGroups - kQStages]), 1);
+    tc::fence_mbar_init();
+  }
+#else
   if (warp == 0 && lane == 0) {
     tc::prefetch_tmap(&p.tmQ); tc::prefetch_tmap(&p.tmKV); tc::prefetch_tmap(&p.tmO);
 #pragma unroll
@@ -127,6 +142,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_fwd_tc_kernel(const __grid_
     for (int i = 0; i < kQStages; ++i) { tc::mbar_init(smem_u32(&q_full[i]), 1); tc::mbar_init(smem_u32(&q_empty[i]), 1); }
     tc::fence_mbar_init();
   }
+#endif
   if (warp == 1) tc::tmem_alloc(smem_u32(&tmem_slot), kTmemCols);
   if (warp >= 2) {
     // B operand of O = P V is [V | 1]: columns 64..79 of the accumulator then hold the row sum of the ROUNDED P the tensor
@@ -159,6 +175,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_fwd_tc_kernel(const __grid_
           tc::tma_load_3d(smem + kOffKV + kb * kKVBuf + kKVBytes, &p.tmKV, bk, p.C + h * kD, 0, b);
         }
         __syncwarp();
+        if (t == 0) TRACE(0, 0, 13);   // first K|V loads issued
         ++kv_n;
       }
       const int s = t % kQStages;
@@ -215,6 +232,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_fwd_tc_kernel(const __grid_
     for (int t = 0; t < ntiles; ++t) {
       if (t == 0 || s_pos == 0) {
         tc::mbar_wait(smem_u32(&kv_full[s_kvn & 1]), (uint32_t)(s_kvn >> 1) & 1u);
+        if (t == 0) TRACE(1, 0, 5);   // first K|V landed
         ++s_kvn;
       }
       if (++s_pos == tpb) s_pos = 0;
@@ -344,12 +362,17 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_fwd_tc_kernel(const __grid_
       }
       TRACE(2 + g, t, 5);
     }
+#ifdef PEA_EXP_WAITREAD
+    if (issuer) tc::tma_store_wait_read<0>();   // shared memory must outlive the store's READ; the global writes complete by grid end
+#else
     if (issuer) tc::tma_store_wait<0>();
+#endif
     TRACE(2 + g, 63, 6);   // group done (stores complete for the issuer's lane 0)
   }
 
   tc::fence_before_sync();
   __syncthreads();
+  if (warp == 0) TRACE(0, 0, 12);   // all roles done
   if (warp == 1) {
     tc::fence_after_sync();
     tc::tmem_dealloc(tmem, kTmemCols);

@@ -210,11 +210,13 @@ __global__ void __launch_bounds__(kThreads) kd_finalize_kernel(const __grid_cons
   }
 }
 
-// d_grad *= upstream * counted  (or = 0 for a skipped tap).  Exits at once when nothing has to change.
+// d_grad *= (upstream / prescale) * counted  (or = 0 for a skipped tap).  Exits at once when nothing has to change, which
+// is the normal case: the fused pass already scaled by `prescale` (the trainer's loss scale) and autograd's upstream
+// gradient IS that loss scale.
 template <typename T>
 __global__ void __launch_bounds__(kThreads) kd_scale_kernel(const __grid_constant__ KdParams p, const float* __restrict__ upstream,
                                                            const float* __restrict__ out) {
-  const float up = upstream ? upstream[0] : 1.0f;
+  const float up = (upstream ? upstream[0] : 1.0f) * p.grad_scale;   // grad_scale carries 1 / prescale here
   for (int ti = 0; ti < p.ntaps; ++ti) {
     const TapParam& tp = p.tap[ti];
     if (!tp.g) continue;
@@ -290,11 +292,13 @@ extern "C" int pea_kd_mse_fwd_bwd(const pea_kd_tap* taps, int ntaps, int B, pea_
 }
 
 extern "C" int pea_kd_scale_grads(const pea_kd_tap* taps, int ntaps, int B, pea_dtype dtype, const float* d_upstream,
-                                  const float* d_out, void* stream) {
+                                  float inv_prescale, const float* d_out, void* stream) {
   KdParams p{};
   int rc = fill_params(p, taps, ntaps, B, dtype);
   if (rc != PEA_OK) return rc;
   PEA_CHECK_ARG(d_out, "kd: out must not be null");
+  PEA_CHECK_ARG(inv_prescale > 0.0f, "kd: inv_prescale must be > 0");
+  p.grad_scale = inv_prescale;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int grid = num_sms() * 8;
   switch (dtype) {

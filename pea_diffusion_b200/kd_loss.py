@@ -23,14 +23,14 @@ Tensor = torch.Tensor
 class _KDLossFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, feature_weight: float, skip_nonfinite: bool, noise: Tensor, pred_t: Tensor, zh: Tensor, nfeat: int,
-                pred: Tensor, *feats: Tensor):
+                pred: Tensor, grad_prescale: float, *feats: Tensor):
         fs, ft = feats[:nfeat], feats[nfeat:]
         dt = pred.dtype
         B = pred.shape[0]
         dev = pred.device
         w_zh = zh.to(device=dev, dtype=torch.float32).contiguous()
         w_en = (1.0 - w_zh).contiguous()
-        need_grad = any(ctx.needs_input_grad[6:7 + nfeat])
+        need_grad = ctx.needs_input_grad[6] or any(ctx.needs_input_grad[8:8 + nfeat])
 
         def same(t):  # targets follow the student's dtype (the reference upcasts both sides to fp32)
             return t.detach().to(dtype=dt).contiguous()
@@ -48,26 +48,35 @@ class _KDLossFn(torch.autograd.Function):
             g = torch.empty_like(s_c) if need_grad else None
             grads.append(g)
             taps.add(s_c, same(t), w_en, 2, grad=g)
-        out = ops.kd_mse_fwd_bwd(taps, B, dt, feature_weight, 1.0, skip_nonfinite, dev)
+        # d(student) is produced in THIS pass, already multiplied by `grad_prescale` -- the loss scale the caller will
+        # back-propagate -- before it is rounded to the student dtype.  In fp16 the unscaled feature-KD coefficient
+        # 0.1 * 2 / (numel * B) ~ 1e-8 is below the smallest fp16 subnormal; scaling after the rounding (in backward)
+        # could not recover it.  The reference gets the same effect from DeepSpeed's loss scaler (train_sdxl_zh.sh:89).
+        out = ops.kd_mse_fwd_bwd(taps, B, dt, feature_weight, float(grad_prescale), skip_nonfinite, dev)
         ctx.taps, ctx.B, ctx.dt, ctx.dev, ctx.out, ctx.grads, ctx.nfeat = taps, B, dt, dev, out, grads, nfeat
+        ctx.inv_prescale = 1.0 / float(grad_prescale)
         ctx.in_dtypes = [pred.dtype] + [s.dtype for s in fs]
         ctx.mark_non_differentiable(out)
         return out[3].clone(), out
 
     @staticmethod
     def backward(ctx, g_total, _g_out):
-        # d(student) was produced for upstream == 1; rescale on the device (a no-op kernel exit when it is 1 and no
-        # tap was skipped) -- no host sync.
+        # d(student) was produced for upstream == grad_prescale; rescale by upstream / grad_prescale on the device (a
+        # no-op kernel exit when that is 1 and no tap was skipped) -- no host sync.
         up = g_total.detach().to(torch.float32).reshape(1).contiguous()
-        ops.kd_scale_grads(ctx.taps, ctx.B, ctx.dt, up, ctx.out, ctx.dev)
+        ops.kd_scale_grads(ctx.taps, ctx.B, ctx.dt, up, ctx.out, ctx.dev, inv_prescale=ctx.inv_prescale)
         gs = [g if g is None or g.dtype == d else g.to(d) for g, d in zip(ctx.grads, ctx.in_dtypes)]
-        return (None, None, None, None, None, None, gs[0], *gs[1:], *([None] * ctx.nfeat))
+        return (None, None, None, None, None, None, gs[0], None, *gs[1:], *([None] * ctx.nfeat))
 
 
 def kd_loss(noise_pred: Tensor, noise: Tensor, noise_pred_teacher: Tensor, feats_student: Sequence[Tensor],
             feats_teacher: Sequence[Tensor], zh_or_not: Tensor, feature_weight: float = 0.1,
-            skip_nonfinite: bool = False) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+            skip_nonfinite: bool = False, grad_prescale: float = 1.0) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
     """-> (total, L0, L1, L2) as 0-dim fp32 device tensors; ``total.backward()`` yields d(noise_pred), d(feats_student).
+
+    ``grad_prescale``: the loss scale the caller is going to back-propagate (``(total * S).backward()``); pass it when
+    training in fp16 so the fused pass scales the gradient before rounding it.  The returned losses are unscaled, and
+    any other upstream gradient still gives the exact result (one extra rescale pass).
 
     ``zh_or_not`` is the batch's int64 [B] language flag (utils/custom_dataset_sdxl.py collate, train_sdxl_zh.py:399).
     Tensors are NCHW [B, ...]; teacher-side tensors get no gradient (``no_grad`` in the reference, :410-415).
@@ -76,5 +85,5 @@ def kd_loss(noise_pred: Tensor, noise: Tensor, noise_pred_teacher: Tensor, feats
     if len(feats_student) != len(feats_teacher):
         raise ValueError("feats_student / feats_teacher length mismatch")
     total, out = _KDLossFn.apply(float(feature_weight), bool(skip_nonfinite), noise, noise_pred_teacher, zh_or_not,
-                                 len(feats_student), noise_pred, *feats_student, *feats_teacher)
+                                 len(feats_student), noise_pred, float(grad_prescale), *feats_student, *feats_teacher)
     return total, out[0], out[1], out[2]

@@ -47,6 +47,11 @@ class KernelTimer:
 
 TIMER = KernelTimer()
 
+# Measurement-only switch (bench.py's `roofline.in_step_marginal`): when set, attn2_fwd / attn2_bwd allocate their outputs
+# but launch nothing, so that the device time of a captured step WITHOUT the attention launches can be subtracted from
+# the time of the full step.  Never set on a product path; outputs are uninitialised memory while it is on.
+SKIP_ATTN2 = False
+
 
 class _timed:
     def __init__(self, name: str, nbytes: int, flops: int = 0):
@@ -221,8 +226,9 @@ def attn2_fwd(q: Tensor, kv: Tensor, heads: int, scale: float) -> Tensor:
     o = torch.empty(B, N, Cq, device=q.device, dtype=q.dtype)
     d = _attn_desc(q, kv, heads, scale)
     d.d_o, d.ld_o = o.data_ptr(), Cq
-    es = q.element_size()
-    with _timed("attn2_fwd", 2 * B * N * Cq * es + 2 * B * L * Cq * es, 4 * B * N * L * Cq):
+    if SKIP_ATTN2:
+        return o
+    with _timed("attn2_fwd", attn2_bytes(B, N, L, Cq, q.element_size())[0], 4 * B * N * L * Cq):
         check(lib.pea_attn2_fwd(C.byref(d), stream_ptr(q.device)), "pea_attn2_fwd")
     return o
 
@@ -245,11 +251,18 @@ def attn2_bwd(q: Tensor, kv: Tensor, do: Tensor, heads: int, scale: float, dkv: 
     d.d_dq, d.ld_dq = dq.data_ptr(), Cq
     d.d_dk, d.d_dv = dkv.data_ptr(), dkv.data_ptr() + 4 * Cq
     d.ld_dkv, d.bs_dkv = dkv.stride(1), dkv.stride(0)
-    es = q.element_size()
-    # read Q, dO, write dQ; read K, V; accumulate dK, dV (fp32 here: 2 * 4 bytes)
-    with _timed("attn2_bwd", 3 * B * N * Cq * es + 2 * B * L * Cq * es + 2 * B * L * Cq * 4, 10 * B * N * L * Cq):
+    if SKIP_ATTN2:
+        return dq, dkv
+    with _timed("attn2_bwd", attn2_bytes(B, N, L, Cq, q.element_size())[1], 10 * B * N * L * Cq):
         check(lib.pea_attn2_bwd(C.byref(d), stream_ptr(q.device)), "pea_attn2_bwd")
     return dq, dkv
+
+
+def attn2_bytes(B: int, N: int, L: int, C: int, es: int = 2):
+    """Algorithmic HBM bytes of one attn2 core call, SURVEY.md section 8d: forward = read Q, write O, read K, V;
+    backward = read Q, dO, write dQ, read K, V, write dK, dV.  (dK / dV are really accumulated in fp32 -- 8 bytes per
+    element instead of the formula's 2 x e -- which the roofline figures do NOT credit.)  -> (fwd, bwd)."""
+    return 2 * B * N * C * es + 2 * B * L * C * es, 3 * B * N * C * es + 4 * B * L * C * es
 
 
 def _attn_desc(q: Tensor, kv: Tensor, heads: int, scale: float) -> Attn2Desc:
@@ -306,6 +319,7 @@ def kd_mse_fwd_bwd(taps: KdTaps, B: int, dtype: torch.dtype, feature_weight: flo
     return out
 
 
-def kd_scale_grads(taps: KdTaps, B: int, dtype: torch.dtype, upstream: Optional[Tensor], out: Tensor, device: torch.device) -> None:
-    check(lib.pea_kd_scale_grads(taps.arr, taps.n, B, dtype_code(dtype), ptr(upstream), out.data_ptr(), stream_ptr(device)),
-          "pea_kd_scale_grads")
+def kd_scale_grads(taps: KdTaps, B: int, dtype: torch.dtype, upstream: Optional[Tensor], out: Tensor, device: torch.device,
+                   inv_prescale: float = 1.0) -> None:
+    check(lib.pea_kd_scale_grads(taps.arr, taps.n, B, dtype_code(dtype), ptr(upstream), float(inv_prescale), out.data_ptr(),
+                                 stream_ptr(device)), "pea_kd_scale_grads")

@@ -61,11 +61,17 @@ def run_oracle_step(case) -> Tuple[Tuple[float, float, float, float], Dict[str, 
     return (float(loss), float(l0), float(l1), float(l2)), {k: v.grad.detach() for k, v in sd.items()}
 
 
-def build_product(case, device="cuda:0", dtype=torch.bfloat16, adapter_precision=None):
+def build_product(case, device="cuda:0", dtype=torch.bfloat16, adapter_precision=None, fused=True):
+    """``fused=False`` keeps the stock processors (torch SDPA -- what the reference runs) in the same shell: the
+    comparison that isolates the attn2 kernels from the shell's own bf16 rounding."""
     from pea_diffusion_b200 import adapter as A, attn2
     s, t = _unets(case, device, dtype)
-    attn2.install(s, freeze=True)
-    attn2.install(t, freeze=True)
+    if fused:
+        attn2.install(s, freeze=True)
+        attn2.install(t, freeze=True)
+    else:
+        s.requires_grad_(False)
+        t.requires_grad_(False)
     in_dim, hidden = case["dims"]
     sd = case["adapter_sd"]
     if case["variant"] == "sdxl":
@@ -88,9 +94,9 @@ def device_batch(case, device, dtype):
     return out
 
 
-def run_product_step(case, device="cuda:0", dtype=torch.bfloat16, adapter_precision=None):
+def run_product_step(case, device="cuda:0", dtype=torch.bfloat16, adapter_precision=None, fused=True):
     from pea_diffusion_b200.train import KDTaps, kd_forward
-    s, t, m = build_product(case, device, dtype, adapter_precision)
+    s, t, m = build_product(case, device, dtype, adapter_precision, fused)
     taps_s, taps_t = KDTaps(s), KDTaps(t)
     loss, l0, l1, l2 = kd_forward(s, t, m, device_batch(case, device, dtype), taps_s, taps_t, case["variant"])
     loss.backward()

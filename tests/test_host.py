@@ -146,6 +146,19 @@ def test_bench_reference_arm_prints_one_json_line():
     assert d["impl"] == "reference" and d["metric"] == "SDXL-1024 KD train samples/s" and d["unit"] == "samples/s"
     assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["higher_is_better"] is True
+    # the reference arm must not map any of this repo's native code into its process
+    assert d["native_libs_mapped"] == [], d["native_libs_mapped"]
+
+
+def test_shell_and_oracle_import_without_binding_the_library():
+    """Only the product modules bind libpea_b200.so (and fail loudly without it); the plain-PyTorch UNet shell that hosts
+    the path and the oracle stay importable on their own -- that is what keeps the CPU reference arm free of our kernels."""
+    code = ("import sys; sys.path.insert(0, %r); import pea_diffusion_b200.shell.unet, oracle.pea_oracle; "
+            "assert 'pea_diffusion_b200._lib' not in sys.modules; "
+            "assert not any('libpea_b200' in l for l in open('/proc/self/maps')); "
+            "import pea_diffusion_b200 as p; p.MLP; assert 'pea_diffusion_b200._lib' in sys.modules; print('ok')" % ROOT)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
 
 
 def test_batch_stager_needs_cuda():
@@ -178,6 +191,10 @@ def test_attn2_group_layout_and_weight_cache_on_host_modules():
         attns[2].to_v.weight.mul_(2.0)                                                           # version bump -> rebuilt
     w2 = g.weights(torch.float32, torch.device("cpu"))
     assert w2 is not w and torch.equal(w2[448:], attns[2].to_v.weight)
+    assert not g.supported(torch.bfloat16)      # trainable to_k / to_v under autograd: the fused path forms no dWk / dWv
+    for a in attns:
+        a.requires_grad_(False)
+    g._supported = None
     assert g.supported(torch.bfloat16)
     attns[0].to_k.lora_layer = object()
     g._supported = None

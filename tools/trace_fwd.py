@@ -17,8 +17,12 @@ H, B, L = Cc // 64, 8, 77
 q = torch.randn(B, N, Cc, device="cuda", dtype=torch.bfloat16)
 kv = torch.randn(B, L, 2 * Cc, device="cuda", dtype=torch.bfloat16)
 scratch = torch.empty(256 << 20, device="cuda", dtype=torch.uint8)
+WARM = len(sys.argv) > 3 and sys.argv[3] == "warm"   # Q freshly written (L2-resident), as inside a training step
+src = torch.randn(B, N, Cc, device="cuda", dtype=torch.bfloat16)
 for _ in range(3):
     scratch.view(torch.int32).sum()
+    if WARM:
+        q.copy_(src)
     ops.attn2_fwd(q, kv, H, 0.125)
 torch.cuda.synchronize()
 n = 16 * 64 * 16
@@ -27,8 +31,9 @@ dll = C.CDLL(_lib.LIB_PATH)
 assert dll.pea_debug_fwd_trace(buf, n) == 0
 ev = lambda role, t, e: buf[(role * 64 + t) * 16 + e]
 t0 = ev(0, 0, 15)
-print(f"N={N} C={Cc}: cycles since kernel entry of CTA 0 (cold L2)")
-print("prologue done", ev(0, 0, 14) - t0)
+print(f"N={N} C={Cc}: cycles since kernel entry of CTA 0 ({'Q in L2' if WARM else 'cold L2'})")
+print("prologue done", ev(0, 0, 14) - t0, "| first K|V TMA issued", ev(0, 0, 13) - t0, "| K|V landed", ev(1, 0, 5) - t0,
+      "| Q0 landed", ev(1, 0, 1) - t0, "| all roles done", ev(0, 0, 12) - t0)
 ntiles = (B * H * ((N + 127) // 128) + 147) // 148
 for t in range(min(ntiles, 12)):
     g = t % 3   # three softmax groups, tiles dealt round-robin (roles 2, 3, 4 in the trace buffer)
