@@ -250,6 +250,15 @@ def _guard_stdout():
         os.dup2(2, 1)
 
 
+def log(msg: str) -> None:
+    """Progress to stderr (a hung phase must be locatable from the driver's stderr tail)."""
+    sys.stderr.write("[bench %7.1fs] %s\n" % (time.perf_counter() - _T0, msg))
+    sys.stderr.flush()
+
+
+_T0 = time.perf_counter()
+
+
 def emit(line: dict) -> None:
     out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
     out.write(json.dumps(line) + "\n")
@@ -263,8 +272,12 @@ def capture_fb(trainer, timer_external=False):
     side.wait_stream(torch.cuda.current_stream())
     g = torch.cuda.CUDAGraph()
     world, trainer.reducer.world = trainer.reducer.world, 1      # measurement graphs carry no NCCL nodes
-    n0 = _lib.launch_count()
     try:
+        with torch.cuda.stream(side):     # one eager pass on the capture stream first (as KDTrainer._capture does): per-pass caches
+            trainer._forward_backward(trainer._static_in)   # and autograd state are then owned by this stream, not by an old graph
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        n0 = _lib.launch_count()
         if timer_external:
             ops.TIMER.reset(True, external=True)
         with torch.cuda.graph(g, stream=side):
@@ -543,11 +556,13 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms) / steps
 
+    log('models built; warm-up (graph capture)')
     warm = max(args.warmup, 3)
     for _ in range(warm):
         trainer.step(dbatch)
     torch.cuda.synchronize()
 
+    log('timed region')
     # ---- value: inputs resident in HBM ------------------------------------------------------------------------
     clocks = ClockSampler(local) if rank == 0 else None
     ops.TIMER.reset(not graph_mode)
@@ -561,6 +576,7 @@ def main():
     ops.TIMER.reset(False)
     timing_note = "CUDA events around every launch inside the timed eager steps"
     marginal, ev_overhead_us = None, None
+    log('timed region done: %.2f ms/step' % ms_step)
     if graph_mode and not args.timed_only:
         # Per-kernel times INSIDE a replayed step: the same forward+backward captured once more with event-record nodes
         # around every library launch; serial schedule (no teacher/student overlap) so each kernel has the GPU to itself.
@@ -572,6 +588,7 @@ def main():
             timing_note = ("CUDA events recorded as event-record nodes around every library launch inside %d replays of a CUDA graph "
                            "of the step's forward+backward (captured after the timed region, serial schedule: no teacher/student overlap, "
                            "no collectives), so the brackets include the node-to-node launch latency" % prof_steps)
+            log('in-graph per-kernel profile done; marginal (skip-attn2) captures')
             t_full, t_skip = in_step_marginal(trainer)
             marginal = (t_full, t_skip)
             ev_overhead_us = event_pair_overhead_us(dev)
@@ -579,6 +596,7 @@ def main():
             trainer.teacher_stream = overlap_stream
         torch.cuda.empty_cache()
 
+    log('e2e loop')
     # ---- e2e: pinned host inputs -> H2D every step, loss read back D2H every step -------------------------------
     host_loss = torch.empty(4, dtype=torch.float32).pin_memory()
 
@@ -593,6 +611,7 @@ def main():
         ms_e2e = timed(e2e_step, args.steps)
     h2d = sum(v.numel() * v.element_size() for v in hbatch.values())
 
+    log('strong-scaling sub-run')
     # ---- strong scaling (configs[2]): global batch 64 -> 64/W per rank in micro-batches of `--batch` ------------------
     strong = None
     if args.global_batch and not args.timed_only and args.global_batch % (world * B) == 0:
@@ -603,6 +622,7 @@ def main():
         strong = {"global_batch": args.global_batch, "per_rank_batch": micro * B, "micro_batches_per_step": micro, "steps": s_steps,
                   "ms_per_step": ms_strong, "value": args.global_batch / (ms_strong * 1e-3), "unit": UNIT, "scaling": "strong",
                   "note": "one optimizer step per global batch; gradients of the micro-batches accumulated on the device"}
+    log('dp check')
     clk = clocks.stop() if clocks else None
     same, sums = parameter_checksums(adapter)
     loss_now = [float(v) for v in trainer.step(dbatch).float().cpu()]
@@ -678,6 +698,7 @@ def main():
         if not args.no_sweep and not args.tiny:
             clocks2 = ClockSampler(local)
             try:
+                log('attn2 / gemm sweeps')
                 roof["sweep"] = attn2_sweep(dev, pk["hbm_gbs"])
                 roof["sweep_gemm"] = gemm_sweep(dev)
                 roof["sweep_how"] = ("each launch alone, 5 warm-up + 20 timed iterations, CUDA events on the launching stream, L2 flushed by "
@@ -687,11 +708,13 @@ def main():
             roof["sweep_clocks"] = clocks2.stop()
         if not args.no_infer and not args.tiny:
             try:
+                log('inference sub-run')
                 line["infer"] = infer_subrun(dev)
             except Exception as exc:
                 line["infer"] = {"error": str(exc).splitlines()[0][:200]}
         if not args.no_cpu_baseline:
             try:
+                log('cpu baseline sample')
                 cl, cb = (16, 2) if args.tiny else (32, 1)
                 sec, cores = cpu_reference_sample(2, 1, cl, cb, args.tiny)
                 scale = (latent / cl) ** 2

@@ -28,6 +28,15 @@ extern "C" {
 #define PEA_B200_VERSION 100 /* 0.1.0 */
 
 enum { PEA_OK = 0, PEA_EINVAL = -1, PEA_ECUDA = -2, PEA_ENODEV = -3, PEA_EUNSUPPORTED = -4 };
+/* `flags` of pea_gemm_desc / pea_attn2_desc.
+ * PEA_LAUNCH_PDL: launch the kernel as a PROGRAMMATIC DEPENDENT of the kernel that precedes it in the stream
+ * (cudaLaunchAttributeProgrammaticStreamSerialization): its prologue -- barrier init, TMEM allocation, descriptor
+ * prefetch -- overlaps that kernel's tail, and every global-memory access is ordered after that kernel's completion by
+ * griddepcontrol.wait.  Every tcgen05 kernel of the library also issues griddepcontrol.launch_dependents right after
+ * its own wait, so a chain  to_q GEMM -> attn2 core -> to_out GEMM  (diffusers AttnProcessor2_0's q = to_q(h);
+ * o = SDPA(...); out = to_out[0](o)) runs without the launch gaps and prologues between its links.  Without the flag
+ * both instructions are no-ops and the launch is an ordinary stream-ordered one. */
+enum { PEA_LAUNCH_PDL = 1 };
 typedef enum { PEA_F32 = 0, PEA_F16 = 1, PEA_BF16 = 2 } pea_dtype;
 
 int pea_version(void);
@@ -92,6 +101,7 @@ typedef struct {
   const void* d_do; long long ld_do;
   void* d_dq; long long ld_dq;
   float* d_dk; float* d_dv; long long ld_dkv, bs_dkv;
+  unsigned flags;          /* PEA_LAUNCH_* */
 } pea_attn2_desc;
 
 int pea_attn2_fwd(const pea_attn2_desc* desc, void* stream);
@@ -129,6 +139,7 @@ typedef struct {
   void* d_out0; pea_dtype out0_dtype; long long ldo0; int out0_accumulate;
   void* d_out1[3]; int out1_nsplit; pea_dtype out1_dtype; long long ldo1;
   int split_k;              /* 0 or 1: none */
+  unsigned flags;           /* PEA_LAUNCH_* */
 } pea_gemm_desc;
 
 int pea_gemm(const pea_gemm_desc* desc, void* stream);

@@ -16,6 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PEA_B200_LIB") or os.path.join(_HERE, "libpea_b200.so")   # override: instrumented debug builds
 
 PEA_F32, PEA_F16, PEA_BF16 = 0, 1, 2
+PEA_LAUNCH_PDL = 1
 KD_MAX_TAPS = 16
 
 _DTYPE = {torch.float32: PEA_F32, torch.float16: PEA_F16, torch.bfloat16: PEA_BF16}
@@ -50,6 +51,7 @@ class Attn2Desc(C.Structure):
         ("d_do", C.c_void_p), ("ld_do", C.c_longlong),
         ("d_dq", C.c_void_p), ("ld_dq", C.c_longlong),
         ("d_dk", C.c_void_p), ("d_dv", C.c_void_p), ("ld_dkv", C.c_longlong), ("bs_dkv", C.c_longlong),
+        ("flags", C.c_uint),
     ]
 
 
@@ -67,6 +69,7 @@ class GemmDesc(C.Structure):
         ("d_out0", C.c_void_p), ("out0_dtype", C.c_int), ("ldo0", C.c_longlong), ("out0_accumulate", C.c_int),
         ("d_out1", C.c_void_p * 3), ("out1_nsplit", C.c_int), ("out1_dtype", C.c_int), ("ldo1", C.c_longlong),
         ("split_k", C.c_int),
+        ("flags", C.c_uint),
     ]
 
 

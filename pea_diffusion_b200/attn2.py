@@ -11,7 +11,10 @@ Reference call path: ``train_sdxl_zh.py:397`` (student, a
   * backward: dQ and dK/dV from the fused backward kernel (S, P recomputed; no O / LSE re-read), then
     dContext = [dK | dV] @ [Wk; Wv] as one GEMM.  The projection weights are frozen: no weight gradient is ever
     formed (the reference computes and discards them -- SURVEY.md D6).
-``to_q`` / ``to_out`` stay the module's own ``nn.Linear`` calls (cuBLAS; out of the hot-path scope, row K4).
+``to_q`` / ``to_out[0]`` run on the same tcgen05 GEMM with the bias in its epilogue, and the three
+kernels of a layer -- to_q GEMM, attention core, to_out GEMM -- are launched as programmatic dependents of each other
+(PEA_LAUNCH_PDL) so the attention kernel's prologue hides under its own producer's tail; ``own_projections=False`` keeps
+the module's ``nn.Linear`` calls (cuBLAS).  The residual add is outside the processor in diffusers' block, so it stays there.
 """
 from __future__ import annotations
 
@@ -57,6 +60,35 @@ class _Attn2Fn(torch.autograd.Function):
             dctx = torch.empty(B, L, Dc, device=q.device, dtype=q.dtype)
             ops.gemm(planes, [wkv], B * L, Dc, wkv.shape[0], b_kmajor=False, out0=dctx.view(B * L, Dc))
         return (dq if ctx_.needs_input_grad[0] else None), dctx, None, None, None, None
+
+
+class _FrozenLinearFn(torch.autograd.Function):
+    """y = x W^T (+ b) for a FROZEN ``nn.Linear`` (``attn.to_q`` / ``attn.to_out[0]``, SURVEY.md kernel K4) on the library's
+    tcgen05 GEMM: bias in the epilogue, dx = dy W in the backward, no weight / bias gradient (the reference forms and
+    discards them).  Launched with PEA_LAUNCH_PDL so that  to_q -> attn2 core -> to_out  (and the mirrored
+    chain of the backward) runs as programmatic dependents: each kernel's prologue overlaps its predecessor's tail."""
+
+    @staticmethod
+    def forward(ctx_, x: Tensor, w: Tensor, b32: Optional[Tensor]):
+        shp = x.shape
+        x2 = x.reshape(-1, shp[-1])
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        y = torch.empty(x2.shape[0], w.shape[0], device=x.device, dtype=x.dtype)
+        ops.gemm([x2], [w], x2.shape[0], w.shape[0], w.shape[1], bias=b32, out0=y, pdl=True)
+        ctx_.save_for_backward(w)
+        ctx_.shape = shp
+        return y.view(*shp[:-1], w.shape[0])
+
+    @staticmethod
+    def backward(ctx_, dy: Tensor):
+        (w,) = ctx_.saved_tensors
+        dy2 = dy.reshape(-1, w.shape[0])
+        if not dy2.is_contiguous():
+            dy2 = dy2.contiguous()
+        dx = torch.empty(dy2.shape[0], w.shape[1], device=dy.device, dtype=dy.dtype)
+        ops.gemm([dy2], [w], dy2.shape[0], w.shape[1], w.shape[0], b_kmajor=False, out0=dx, pdl=True)
+        return dx.view(ctx_.shape), None, None
 
 
 class _ProjectAllFn(torch.autograd.Function):
@@ -109,10 +141,12 @@ class _Attn2GroupedFn(torch.autograd.Function):
     """One layer's attention core on its column slice of the group's K|V tensor."""
 
     @staticmethod
-    def forward(ctx_, q: Tensor, token: Optional[Tensor], kv: Tensor, group: "Attn2Group", layer: int, heads: int, scale: float):
-        o = ops.attn2_fwd(q, kv, heads, scale)
+    def forward(ctx_, q: Tensor, token: Optional[Tensor], kv: Tensor, group: "Attn2Group", layer: int, heads: int, scale: float,
+                pdl: bool = False):
+        o = ops.attn2_fwd(q, kv, heads, scale, pdl=pdl)
         ctx_.save_for_backward(q, kv)
         ctx_.group, ctx_.layer, ctx_.heads, ctx_.scale, ctx_.has_token = group, layer, heads, scale, token is not None
+        ctx_.pdl = pdl
         ctx_.state = group.state
         ctx_.track = ctx_.state is not None and ctx_.state.dkv_all is not None
         if ctx_.track:
@@ -127,10 +161,10 @@ class _Attn2GroupedFn(torch.autograd.Function):
         if ctx_.track:
             off, c2 = group.offsets[ctx_.layer], group.widths[ctx_.layer]
             dkv = state.dkv_all[:, :, off:off + c2]
-        dq, _ = ops.attn2_bwd(q, kv, do, ctx_.heads, ctx_.scale, dkv=dkv)
+        dq, _ = ops.attn2_bwd(q, kv, do, ctx_.heads, ctx_.scale, dkv=dkv, pdl=ctx_.pdl)
         if ctx_.track:
             state.bwd_calls += 1
-        return (dq if ctx_.needs_input_grad[0] else None), (do.new_zeros(1) if ctx_.has_token else None), None, None, None, None, None
+        return (dq if ctx_.needs_input_grad[0] else None), (do.new_zeros(1) if ctx_.has_token else None), None, None, None, None, None, None
 
 
 class _PassState:
@@ -237,10 +271,15 @@ class PEAAttn2Processor:
 
     _warned = False
 
-    def __init__(self, fallback=None, cache_kv: bool = False, group: Optional[Attn2Group] = None):
+    def __init__(self, fallback=None, cache_kv: bool = False, group: Optional[Attn2Group] = None, own_projections: bool = False):
         self.fallback = fallback
         self.cache_kv = cache_kv
         self.group = group
+        # to_q / to_out[0] on the library's GEMM (bias in the epilogue) as a PDL chain around the attention kernel; False
+        # keeps the module's own nn.Linear calls (cuBLAS)
+        self.own_projections = own_projections
+        self._bias32: Optional[Tensor] = None
+        self._bias_key = None
         self._wkv: Optional[Tensor] = None
         self._wkv_key = None
         self._kv: Optional[Tensor] = None
@@ -254,6 +293,24 @@ class PEAAttn2Processor:
             self._wkv = torch.cat([wk.detach(), wv.detach()], dim=0).to(dtype).contiguous()
             self._wkv_key = key
         return self._wkv
+
+    def _linear(self, lin, x: Tensor, scale: float, is_out: bool) -> Tensor:
+        """``lin(x)`` -- through the library's GEMM when ``lin`` is a plain frozen 16-bit Linear (no LoRA layer, weight in the
+        activation dtype, TMA-compatible sizes), else the module's own forward (diffusers 0.23 LoRACompatibleLinear takes
+        ``scale`` as a second positional argument only when a lora_layer is attached)."""
+        w = lin.weight
+        own = (self.own_projections and getattr(lin, "lora_layer", None) is None and w.dtype == x.dtype and
+               not (torch.is_grad_enabled() and (w.requires_grad or (lin.bias is not None and lin.bias.requires_grad))) and
+               w.shape[0] % 8 == 0 and w.shape[1] % 8 == 0 and w.is_contiguous() and w.data_ptr() % 16 == 0)
+        if not own:
+            return lin(x)
+        b32 = None
+        if lin.bias is not None:
+            key = (lin.bias.data_ptr(), lin.bias._version)
+            if self._bias32 is None or self._bias_key != key:
+                self._bias32, self._bias_key = lin.bias.detach().float().contiguous(), key
+            b32 = self._bias32
+        return _FrozenLinearFn.apply(x, w.detach(), b32)
 
     def _supported(self, attn, hidden_states, encoder_hidden_states, attention_mask) -> bool:
         if encoder_hidden_states is None or attention_mask is not None:
@@ -287,7 +344,7 @@ class PEAAttn2Processor:
             return self.fallback(attn, hidden_states, encoder_hidden_states=encoder_hidden_states,
                                  attention_mask=attention_mask, temb=temb, scale=scale)
         dt = hidden_states.dtype
-        q = attn.to_q(hidden_states)
+        q = self._linear(attn.to_q, hidden_states, scale, False)
         if self.group is not None and id(attn) in self.group.index and self.group.supported(dt):
             # all layers' K|V from ONE projection GEMM per forward pass (and per denoise loop when the context is reused)
             B, L, _ = encoder_hidden_states.shape
@@ -295,8 +352,8 @@ class PEAAttn2Processor:
             kv_all, token = self.group.project(encoder_hidden_states, dt, i)
             off, c2 = self.group.offsets[i], self.group.widths[i]
             kv = kv_all.view(B, L, self.group.total)[:, :, off:off + c2]
-            o = _Attn2GroupedFn.apply(q, token, kv, self.group, i, attn.heads, float(attn.scale))
-            o = attn.to_out[0](o)
+            o = _Attn2GroupedFn.apply(q, token, kv, self.group, i, attn.heads, float(attn.scale), self.own_projections)
+            o = self._linear(attn.to_out[0], o, scale, True)
             return attn.to_out[1](o)
         context = encoder_hidden_states.to(dt)
         if not context.is_contiguous():
@@ -314,11 +371,12 @@ class PEAAttn2Processor:
                 self._kv_key = key
             kv = self._kv
         o = _Attn2Fn.apply(q, context, wkv, attn.heads, float(attn.scale), kv)
-        o = attn.to_out[0](o)
+        o = self._linear(attn.to_out[0], o, scale, True)
         return attn.to_out[1](o)
 
 
-def install(unet, freeze: bool = True, cache_kv: bool = False, group_projection: bool = True) -> Dict[str, object]:
+def install(unet, freeze: bool = True, cache_kv: bool = False, group_projection: bool = True,
+            own_projections: bool = False) -> Dict[str, object]:
     """``unet.set_attn_processor({...})`` with ``PEAAttn2Processor`` on every ``*.attn2`` module and the existing
     processor kept everywhere else (diffusers requires the dict to cover every attention module).
 
@@ -338,7 +396,8 @@ def install(unet, freeze: bool = True, cache_kv: bool = False, group_projection:
             group = Attn2Group(attns)
     procs = {}
     for name, proc in current.items():
-        procs[name] = PEAAttn2Processor(fallback=proc, cache_kv=cache_kv, group=group) if name.endswith("attn2.processor") else proc
+        procs[name] = (PEAAttn2Processor(fallback=proc, cache_kv=cache_kv, group=group, own_projections=own_projections)
+                       if name.endswith("attn2.processor") else proc)
     unet.set_attn_processor(procs)
     if freeze:
         unet.requires_grad_(False)

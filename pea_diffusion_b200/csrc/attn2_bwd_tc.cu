@@ -33,7 +33,12 @@ namespace {
 
 constexpr int kQT = 128, kD = 64, kLP = 80;
 constexpr int kRing = 3;
+#ifdef PEA_BWD_SPLIT
+constexpr int kThreads = 384;   // + warp 11: the S / dP issuer
+#else
 constexpr int kThreads = 352;
+#endif
+constexpr int kSdpWarp = 11;
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kTS = 0, kTdP = 80, kTPair = 160, kTdQ = 320, kTdKV = 384;
 constexpr uint32_t kLaneDK = 16u << 16;        // dK^T sits 16 lanes below dV^T in every quarter
@@ -84,6 +89,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_bwd_tc_kernel(const __grid_
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t kv_full[2], kv_empty[2], ring_full[kRing], ring_empty[kRing];
   __shared__ __align__(8) uint64_t sdp_full[2], ds_ready[2], pds_free, dq_full, dq_free, dkv_full, dkv_free, dq_staged, stage_free;
+  __shared__ __align__(8) uint64_t dq_done[2];   // per group: dQ(t) has consumed dS from dP[g] -> S / dP(t+2) may overwrite S[g], dP[g]
   __shared__ uint32_t tmem_slot;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -106,6 +112,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_bwd_tc_kernel(const __grid_
     }
 #pragma unroll
     for (int i = 0; i < kRing; ++i) { tc::mbar_init(smem_u32(&ring_full[i]), 1); tc::mbar_init(smem_u32(&ring_empty[i]), 1); }
+    tc::mbar_init(smem_u32(&dq_done[0]), 1); tc::mbar_init(smem_u32(&dq_done[1]), 1);
     tc::mbar_init(smem_u32(&pds_free), 1);
     tc::mbar_init(smem_u32(&dq_full), 1);
     tc::mbar_init(smem_u32(&dq_free), 4);
@@ -120,6 +127,8 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_bwd_tc_kernel(const __grid_
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem = tmem_slot;
+  pdl_wait();                 // see attn2_tc.cu: the prologue overlapped the preceding kernel's tail under PEA_LAUNCH_PDL
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -151,8 +160,11 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_bwd_tc_kernel(const __grid_
       if (++s == kRing) { s = 0; ring_ph ^= 1u; }
       if (++tile == tpb) { tile = 0; if (++h == p.H) { h = 0; ++b; } }
     }
-  } else if (warp == 1) {
-    // ===== MMA issuer =====
+  } else if (warp == 1 || warp == kSdpWarp) {
+    // ===== MMA issuers.  PEA_BWD_SPLIT: warp 1 issues dQ / dV^T / dK^T, warp 11 issues S / dP -- S / dP(t+2) then starts the
+    // moment dQ(t) has consumed dS (dq_done[g]) instead of queueing behind the 16 dV^T / dK^T MMAs of tile t in one
+    // in-order instruction stream, which put ~1 300 cycles on the critical path of every softmax group
+    // (profiles/r1_attn2_bwd_timeline.txt: sdp_full(t) -> softmax 2 800 -> dQ, dV^T, dK^T 1 300 -> S, dP 1 280 -> sdp_full(t+2)). =====
     // K-major tiles [rows][64 x 16-bit] (Q, dO as A; K, V as B of S / dP): K=16 step = 32 B inside the swizzle atom.
     // MN-major tiles: K, Q, dO as B ([k rows][64 contiguous]): K=16 step = 16 rows = 2048 B;
     //                 P, dS as A ([q rows][keys], two 64-key slabs 16 KiB apart = LBO): K=16 step = 16 q rows = 2048 B.
@@ -191,8 +203,17 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_bwd_tc_kernel(const __grid_
       }
       __syncwarp();
     };
+#ifdef PEA_BWD_SPLIT
+    if (warp == kSdpWarp) {
+      for (int t = 0; t < ntiles; ++t) {
+        if (t >= 2) tc::mbar_wait(smem_u32(&dq_done[t & 1]), (uint32_t)((t >> 1) - 1) & 1u);   // dQ(t-2) done with dP[g]
+        issue_sdp(t);
+      }
+    } else
+#else
     if (ntiles > 0) issue_sdp(0);
     if (ntiles > 1) issue_sdp(1);
+#endif
     for (int t = 0; t < ntiles; ++t) {
       const int g = t & 1, rs = m_rs;
       if (++m_rs == kRing) m_rs = 0;
@@ -219,6 +240,9 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_bwd_tc_kernel(const __grid_
         for (int k = 0; k < kLP / 16; ++k)
           tc::mma_f16_ts(tmem + kTdQ, tds + k * 8, kDescMN | (uint64_t)(ka + k * 128), p.idesc_dq, k > 0);
         tc::mma_commit(smem_u32(&dq_full));
+#ifdef PEA_BWD_SPLIT
+        tc::mma_commit(smem_u32(&dq_done[g]));
+#endif
         // dV^T += dO^T P ; dK^T += Q^T dS   (reduction over the 128 query rows; the two chains interleaved)
 #pragma unroll
         for (int k = 0; k < kQT / 16; ++k) {
@@ -234,7 +258,9 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_bwd_tc_kernel(const __grid_
       }
       __syncwarp();
       if (last_of_bh || last_tile) ++flushes;
+#ifndef PEA_BWD_SPLIT
       if (t + 2 < ntiles) issue_sdp(t + 2);
+#endif
     }
   } else if (warp < 10) {
     // ===== softmax / epilogue groups =====
@@ -414,7 +440,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_bwd_tc_kernel(const __grid_
         ++flushes;
       }
     }
-  } else {
+  } else if (warp == 10) {
     // ===== warp 10: dQ TMA-store issuer =====
     int b = b0, h = h0, tile = rem0;
     for (int t = 0; t < ntiles; ++t) {
@@ -444,10 +470,10 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_bwd_tc_kernel(const __grid_
 }
 
 template <typename T>
-int launch_bwd_tc(const BwdParams& p, int ctas, cudaStream_t st) {
+int launch_bwd_tc(const BwdParams& p, int ctas, cudaStream_t st, bool pdl) {
   static std::atomic<unsigned long long> attr_done{0};
   if (int rc = ensure_dynamic_smem(attn2_bwd_tc_kernel<T>, (int)kSmemBytes, attr_done)) return rc;
-  attn2_bwd_tc_kernel<T><<<ctas, kThreads, kSmemBytes, st>>>(p);
+  PEA_CUDA(launch_ex(attn2_bwd_tc_kernel<T>, ctas, kThreads, kSmemBytes, st, pdl, p));
   PEA_LAUNCH_CHECK();
   return PEA_OK;
 }
@@ -504,7 +530,8 @@ int attn2_bwd_tc(const pea_attn2_desc* a, cudaStream_t st) {
   p.idesc_dq = tc::make_idesc(fmt, 128, kD, 0, 1);
   p.idesc_dkv = tc::make_idesc(fmt, 64, kLP, 1, 1);
   p.dk = a->d_dk; p.dv = a->d_dv; p.ld_dkv = a->ld_dkv; p.bs_dkv = a->bs_dkv;
-  return fp16 ? launch_bwd_tc<__half>(p, ctas, st) : launch_bwd_tc<__nv_bfloat16>(p, ctas, st);
+  const bool pdl = (a->flags & PEA_LAUNCH_PDL) != 0;
+  return fp16 ? launch_bwd_tc<__half>(p, ctas, st, pdl) : launch_bwd_tc<__nv_bfloat16>(p, ctas, st, pdl);
 }
 
 }  // namespace pea

@@ -103,6 +103,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_fwd_tc_kernel(const __grid_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
   if (warp == 0) TRACE(0, 0, 15);   // kernel entry
+  TRACE(15, warp, 0);               // per-warp entry
 
   // ---- this CTA's contiguous range of work items; item = bh * tiles_per_bh + tile ----------------------------------
   const int item0 = blockIdx.x * p.tiles_per_cta;
@@ -154,11 +155,15 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_fwd_tc_kernel(const __grid_
     }
     tc::fence_proxy_async_smem();
   }
+  TRACE(15, warp, 1);               // per-warp: own prologue work done
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem = tmem_slot;
+  TRACE(15, warp, 2);               // per-warp: past the prologue barrier
   if (warp == 0) TRACE(0, 0, 14);   // prologue done (barriers, TMEM)
+  pdl_wait();                 // everything above overlapped the preceding kernel's tail (PEA_LAUNCH_PDL); Q / K|V are its output
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -380,10 +385,10 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_fwd_tc_kernel(const __grid_
 }
 
 template <typename T>
-int launch_fwd_tc(const FwdParams& p, int units, cudaStream_t st) {
+int launch_fwd_tc(const FwdParams& p, int units, cudaStream_t st, bool pdl) {
   static std::atomic<unsigned long long> attr_done{0};
   if (int rc = ensure_dynamic_smem(attn2_fwd_tc_kernel<T>, (int)kSmemBytes, attr_done)) return rc;
-  attn2_fwd_tc_kernel<T><<<units, kThreads, kSmemBytes, st>>>(p);
+  PEA_CUDA(launch_ex(attn2_fwd_tc_kernel<T>, units, kThreads, kSmemBytes, st, pdl, p));
   PEA_LAUNCH_CHECK();
   return PEA_OK;
 }
@@ -431,7 +436,8 @@ int attn2_fwd_tc(const pea_attn2_desc* a, cudaStream_t st) {
   const int units = (p.total_tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
   p.idesc_s = tc::make_idesc(fp16 ? 0 : 1, 128, kLP, 0, 0);
   p.idesc_o = tc::make_idesc(fp16 ? 0 : 1, 128, kNO, 0, 1);
-  return fp16 ? launch_fwd_tc<__half>(p, units, st) : launch_fwd_tc<__nv_bfloat16>(p, units, st);
+  const bool pdl = (a->flags & PEA_LAUNCH_PDL) != 0;
+  return fp16 ? launch_fwd_tc<__half>(p, units, st, pdl) : launch_fwd_tc<__nv_bfloat16>(p, units, st, pdl);
 }
 
 bool attn2_fwd_tc_eligible(const pea_attn2_desc* a) {

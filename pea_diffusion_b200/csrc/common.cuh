@@ -63,7 +63,31 @@ inline int ensure_dynamic_smem(Kernel kernel, int bytes, std::atomic<unsigned lo
   return PEA_OK;
 }
 
+// Launch through cudaLaunchKernelEx; `pdl` adds cudaLaunchAttributeProgrammaticStreamSerialization (the kernel must then
+// order its global-memory accesses with pdl_wait(), below).
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_ex(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, bool pdl, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---- device helpers ------------------------------------------------------------------------------------------
+// Programmatic dependent launch.  pdl_wait(): block until the grid this one was launched behind has completed and its
+// memory is visible (returns at once for an ordinary launch).  pdl_launch_dependents(): allow the NEXT grid in the stream,
+// if it was launched with the PDL attribute, to start its prologue as SM resources free up.  Issued in this order, a
+// running grid implies that everything before its predecessor has completed.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 template <typename T> struct VecTraits;
 
 __device__ __forceinline__ float to_float(float v) { return v; }

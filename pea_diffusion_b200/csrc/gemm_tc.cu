@@ -52,6 +52,7 @@ struct GemmParams {
   int act;
   void* out0; int out0_dtype; long long ldo0; int out0_mode;  // 0 store, 1 +=, 2 atomic add
   void* out1[3]; int out1_nsplit; int out1_dtype; long long ldo1;
+  int pdl;
 };
 
 // ---- epilogue helpers: 8 consecutive columns of one row -----------------------------------------------------------
@@ -272,6 +273,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem_base = tmem_base_slot;
+  pdl_wait();                 // PEA_LAUNCH_PDL: the prologue above overlapped the preceding kernel's tail
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ===== TMA producer (whole warp loops; one elected lane issues) =====
@@ -429,6 +432,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc2_kernel(const __grid_cons
   tc::cluster_sync();            // the peer's barriers exist before anything arrives on them
   tc::fence_after_sync();
   const uint32_t tmem_base = tmem_base_slot;
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ===== TMA producer (both CTAs): own A rows, own half of B; bytes credited to the leader's full barrier =====
@@ -524,7 +529,7 @@ template <int SA, int SB, int A_MN, int B_MN, int BN>
 int launch(const GemmParams& p, int ctas, size_t smem, cudaStream_t st) {
   static std::atomic<unsigned long long> attr_done{0};
   if (int rc = ensure_dynamic_smem(gemm_tc_kernel<SA, SB, A_MN, B_MN, BN>, (int)(kSmemBudget + 1024), attr_done)) return rc;
-  gemm_tc_kernel<SA, SB, A_MN, B_MN, BN><<<ctas, kThreads, smem, st>>>(p);
+  PEA_CUDA(launch_ex(gemm_tc_kernel<SA, SB, A_MN, B_MN, BN>, ctas, kThreads, smem, st, p.pdl != 0, p));
   PEA_LAUNCH_CHECK();
   return PEA_OK;
 }
@@ -548,11 +553,13 @@ int launch_pair(const GemmParams& p, int pairs, size_t smem, cudaStream_t st) {
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = p.pdl ? 2 : 1;
   PEA_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc2_kernel<A_MN, B_MN>, p));
   PEA_LAUNCH_CHECK();
   return PEA_OK;
@@ -620,6 +627,13 @@ int encode_tmap_16bit(CUtensorMap* out, const void* base, int rank, const uint64
   std::lock_guard<std::mutex> lock(mu);
   auto it = cache.find(key);
   if (it != cache.end()) { *out = it->second; return PEA_OK; }
+  {
+    // cuTensorMapEncodeTiled is a DRIVER call and needs a current context on the calling thread.  A thread whose first CUDA
+    // work is one of our launches (an autograd worker starting a backward with a library GEMM) has none yet: the runtime
+    // binds the primary context lazily, on its own first call.  Once per thread.
+    static thread_local bool ctx_bound = false;
+    if (!ctx_bound) { PEA_CUDA(cudaFree(nullptr)); ctx_bound = true; }
+  }
   if (!fn) {
     void* sym = nullptr;
     cudaDriverEntryPointQueryResult qres;
@@ -738,6 +752,7 @@ extern "C" int pea_gemm(const pea_gemm_desc* g, void* stream) {
     p.out1[s] = g->d_out1[s];
   }
   p.out1_nsplit = g->out1_nsplit; p.out1_dtype = g->out1_dtype; p.ldo1 = g->ldo1;
+  p.pdl = (g->flags & PEA_LAUNCH_PDL) ? 1 : 0;
 
   if (pair) {
     const int pairs = p.total_tiles < num_sms() / 2 ? p.total_tiles : num_sms() / 2;

@@ -80,7 +80,7 @@ def gemm(A: Sequence[Tensor], B: Sequence[Tensor], M: int, N: int, K: int, *, a_
          alpha: float = 1.0, bias: Optional[Tensor] = None, aux: Optional[Tensor] = None,
          rowadd: Optional[Tensor] = None, rowadd_group: int = 1, rowadd_scale: float = 1.0, act: bool = False,
          out0: Optional[Tensor] = None, accumulate: bool = False, out1: Optional[Sequence[Tensor]] = None,
-         split_k: int = 0) -> None:
+         split_k: int = 0, pdl: bool = False) -> None:
     """C[m,n] = sum_k A(m,k) B(n,k) on tcgen05 tensor cores; see ``pea_gemm`` in the header for the epilogue.
 
     ``A`` / ``B`` are lists of 1..3 16-bit planes (2-D, unit column stride).  K-major A is stored [M, K]; MN-major A is
@@ -123,6 +123,7 @@ def gemm(A: Sequence[Tensor], B: Sequence[Tensor], M: int, N: int, K: int, *, a_
         d.d_out1 = planes3(out1)
         d.out1_nsplit, d.out1_dtype, d.ldo1 = len(out1), dtype_code(out1[0].dtype), out1[0].stride(0)
     d.split_k = split_k
+    d.flags = _lib.PEA_LAUNCH_PDL if pdl else 0
     nprod = sum(1 for i in range(len(A)) for j in range(len(B)) if i + j < max(len(A), len(B)))
     io = 2 * (len(A) * M * K + len(B) * N * K) + (out0.element_size() * M * N if out0 is not None else 0) + \
         (sum(t.element_size() for t in out1) * M * N if out1 else 0) + (aux.element_size() * M * N if aux is not None else 0)
@@ -218,13 +219,14 @@ def add_noise(latents: Tensor, noise_raw: Tensor, offs: Optional[Tensor], noise_
     return noise, noisy
 
 
-def attn2_fwd(q: Tensor, kv: Tensor, heads: int, scale: float) -> Tensor:
+def attn2_fwd(q: Tensor, kv: Tensor, heads: int, scale: float, pdl: bool = False) -> Tensor:
     """q [B,N,C], kv [B,L,2C] (K in columns [0,C), V in [C,2C)) -> o [B,N,C] = softmax(q k^T scale) v per head."""
     require_cuda(q, kv)
     B, N, Cq = q.shape
     L = kv.shape[1]
     o = torch.empty(B, N, Cq, device=q.device, dtype=q.dtype)
     d = _attn_desc(q, kv, heads, scale)
+    d.flags = _lib.PEA_LAUNCH_PDL if pdl else 0
     d.d_o, d.ld_o = o.data_ptr(), Cq
     if SKIP_ATTN2:
         return o
@@ -233,7 +235,7 @@ def attn2_fwd(q: Tensor, kv: Tensor, heads: int, scale: float) -> Tensor:
     return o
 
 
-def attn2_bwd(q: Tensor, kv: Tensor, do: Tensor, heads: int, scale: float, dkv: Optional[Tensor] = None):
+def attn2_bwd(q: Tensor, kv: Tensor, do: Tensor, heads: int, scale: float, dkv: Optional[Tensor] = None, pdl: bool = False):
     """-> (dq [B,N,C] in q's dtype, dkv [B,L,2C] fp32).  ``dkv`` may be a caller-owned fp32 [B,L,2C] view (unit column
     stride) that is ACCUMULATED into -- e.g. one layer's column slice of a buffer shared by all layers."""
     require_cuda(q, kv, do, dkv)
@@ -247,6 +249,7 @@ def attn2_bwd(q: Tensor, kv: Tensor, do: Tensor, heads: int, scale: float, dkv: 
     elif dkv.dtype != torch.float32 or tuple(dkv.shape) != (B, L, 2 * Cq) or dkv.stride(2) != 1:
         raise ValueError("attn2_bwd: dkv must be an fp32 [B, L, 2C] view with unit column stride")
     d = _attn_desc(q, kv, heads, scale)
+    d.flags = _lib.PEA_LAUNCH_PDL if pdl else 0
     d.d_do, d.ld_do = do.data_ptr(), do.stride(1)
     d.d_dq, d.ld_dq = dq.data_ptr(), Cq
     d.d_dk, d.d_dv = dkv.data_ptr(), dkv.data_ptr() + 4 * Cq

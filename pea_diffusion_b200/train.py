@@ -333,9 +333,10 @@ class KDTrainer:
         self.dynamic_loss_scale = dynamic_loss_scale and loss_scale is not None
         if self.loss_scale is not None:
             dev = params[0].device
-            self._scale = torch.full((1,), self.loss_scale, device=dev, dtype=torch.float32)
-            self._growth = torch.zeros(1, device=dev, dtype=torch.int32)
-            self._found_inf = torch.zeros(1, device=dev, dtype=torch.float32)
+            # 0-dim tensors: what torch's fused AdamW (found_inf) and the amp helpers expect
+            self._scale = torch.full((), self.loss_scale, device=dev, dtype=torch.float32)
+            self._growth = torch.zeros((), device=dev, dtype=torch.int32)
+            self._found_inf = torch.zeros((), device=dev, dtype=torch.float32)
             self._growth_interval = growth_interval
 
     def _forward_backward(self, batch: Mapping[str, Tensor], reduce: bool = True) -> Tensor:
@@ -345,7 +346,7 @@ class KDTrainer:
         if self.loss_scale is None:
             loss.backward()
         else:
-            loss.backward(gradient=self._scale.reshape(()).to(loss.dtype))
+            loss.backward(gradient=self._scale.to(loss.dtype))
         self.taps_s.clear()
         self.taps_t.clear()
         if reduce:

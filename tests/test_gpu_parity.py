@@ -173,10 +173,12 @@ def test_attn2_explicit_vs_sdpa_and_rejects(ops):
         ops.attn2_fwd(q, kv, 2, 0.125)
 
 
+@pytest.mark.parametrize("own", [False, True])
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
-def test_attn2_module_processor_vs_oracle(dtype):
+def test_attn2_module_processor_vs_oracle(dtype, own):
     """Whole attn2 module through the processor protocol (to_q, fused K/V projection + core, to_out) and its gradients
-    w.r.t. hidden states and context, against the oracle's restatement of AttnProcessor2_0."""
+    w.r.t. hidden states and context, against the oracle's restatement of AttnProcessor2_0.  ``own``: to_q / to_out[0] on the
+    library's GEMM (bias in the epilogue) launched as a programmatic-dependent chain around the attention kernel (K4)."""
     from pea_diffusion_b200.attn2 import PEAAttn2Processor
     from pea_diffusion_b200.shell.unet import Attention, StockAttnProcessor
     torch.manual_seed(0)
@@ -192,7 +194,7 @@ def test_attn2_module_processor_vs_oracle(dtype):
                   rnd(attn.to_out[0].bias), H)
     ref.backward(rnd(gout))
     attn = attn.to(device=DEV, dtype=dtype).requires_grad_(False)
-    attn.set_processor(PEAAttn2Processor(fallback=StockAttnProcessor()))
+    attn.set_processor(PEAAttn2Processor(fallback=StockAttnProcessor(), own_projections=own))
     hd = h.to(device=DEV, dtype=dtype).requires_grad_(True)
     cd = ctx.to(device=DEV, dtype=dtype).requires_grad_(True)
     out = attn(hd, encoder_hidden_states=cd)

@@ -23,6 +23,7 @@ ap.add_argument("--C", type=int, default=1280)
 ap.add_argument("--reps", type=int, default=20)
 ap.add_argument("--own-gemm", type=int, default=0, help="1: the producer / consumer GEMMs are pea_gemm (PDL chain when built in)")
 ap.add_argument("--replays", type=int, default=20)
+ap.add_argument("--pdl", type=int, default=0, help="1: every library launch carries PEA_LAUNCH_PDL")
 args = ap.parse_args()
 
 dev = "cuda:0"
@@ -41,7 +42,7 @@ dkv = torch.zeros(B, L, 2 * Cc, device=dev, dtype=torch.float32)
 
 def gemm(a, w, out):
     if args.own_gemm:
-        ops.gemm([a], [w], a.shape[0], w.shape[0], a.shape[1], out0=out)
+        ops.gemm([a], [w], a.shape[0], w.shape[0], a.shape[1], out0=out, pdl=bool(args.pdl))
     else:
         torch.matmul(a, w.t(), out=out)
 
@@ -53,9 +54,9 @@ def body(with_attn, bracket=None):
             if bracket is not None:
                 e0 = torch.cuda.Event(enable_timing=True, external=True); e0.record()
             if args.mode == "fwd":
-                o = ops.attn2_fwd(q.view(B, N, Cc), kv, H, 0.125)
+                o = ops.attn2_fwd(q.view(B, N, Cc), kv, H, 0.125, pdl=bool(args.pdl))
             else:
-                o, _ = ops.attn2_bwd(q.view(B, N, Cc), kv, do, H, 0.125, dkv=dkv)
+                o, _ = ops.attn2_bwd(q.view(B, N, Cc), kv, do, H, 0.125, dkv=dkv, pdl=bool(args.pdl))
             if bracket is not None:
                 e1 = torch.cuda.Event(enable_timing=True, external=True); e1.record()
                 bracket.append((e0, e1))
@@ -99,7 +100,7 @@ br = sorted(e0.elapsed_time(e1) * 1e3 for e0, e1 in pairs)
 es = 2
 nbytes = (2 * B * N * Cc * es + 2 * B * L * Cc * es) if args.mode == "fwd" else (3 * B * N * Cc * es + 4 * B * L * Cc * es)
 marg = (t_with - t_without) / args.reps
-print(json.dumps({"probe": "chain", "mode": args.mode, "N": N, "C": Cc, "own_gemm": args.own_gemm, "lib": os.environ.get("PEA_B200_LIB", "product"),
+print(json.dumps({"probe": "chain", "mode": args.mode, "N": N, "C": Cc, "own_gemm": args.own_gemm, "pdl": args.pdl, "lib": os.environ.get("PEA_B200_LIB", "product"),
                   "graph_with_us": t_with, "graph_without_us": t_without, "marginal_us_per_launch": marg,
                   "bracketed_us_median": br[len(br) // 2], "algorithmic_bytes": nbytes,
                   "marginal_GBps": nbytes / marg / 1e3, "bracketed_GBps": nbytes / br[len(br) // 2] / 1e3}))

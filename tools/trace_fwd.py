@@ -34,6 +34,8 @@ t0 = ev(0, 0, 15)
 print(f"N={N} C={Cc}: cycles since kernel entry of CTA 0 ({'Q in L2' if WARM else 'cold L2'})")
 print("prologue done", ev(0, 0, 14) - t0, "| first K|V TMA issued", ev(0, 0, 13) - t0, "| K|V landed", ev(1, 0, 5) - t0,
       "| Q0 landed", ev(1, 0, 1) - t0, "| all roles done", ev(0, 0, 12) - t0)
+print("per-warp prologue (entry / own work done / past the barrier):",
+      " ".join(f"w{w}:{ev(15, w, 0) - t0}/{ev(15, w, 1) - t0}/{ev(15, w, 2) - t0}" for w in range(15)))
 ntiles = (B * H * ((N + 127) // 128) + 147) // 148
 for t in range(min(ntiles, 12)):
     g = t % 3   # three softmax groups, tiles dealt round-robin (roles 2, 3, 4 in the trace buffer)
