@@ -19,6 +19,7 @@ the module's ``nn.Linear`` calls (cuBLAS).  The residual add is outside the proc
 from __future__ import annotations
 
 import warnings
+import weakref
 from typing import Dict, Optional
 
 import torch
@@ -192,7 +193,12 @@ class Attn2Group:
         self.index = {id(a): i for i, a in enumerate(self.attns)}
         self._wcat: Optional[Tensor] = None
         self._wkey = None
-        self._ctx_ref: Optional[Tensor] = None     # strong reference: identity is the cache key (no address reuse)
+        # WEAK reference to the context tensor object the cache belongs to: identity is the cache key (a dead object can
+        # never alias a new one), and the previous pass's autograd graph -- which hangs off the student's context -- is not
+        # kept alive across passes.  (A strong reference made the next pass re-use that graph's AccumulateGrad nodes, whose
+        # streams belong to an earlier CUDA-graph capture: a second capture of the step then failed with
+        # cudaErrorStreamCaptureIsolation.)
+        self._ctx_ref = None
         self._ctx_key = None
         self._kv_all: Optional[Tensor] = None
         self._token: Optional[Tensor] = None
@@ -234,7 +240,7 @@ class Attn2Group:
         self.weights(dtype, context.device)          # refreshes _wkey: a weight update between passes invalidates cached K|V
         key = (context._version, dtype, need_grad, self._wkey)
         new_pass = need_grad and layer == 0
-        if not new_pass and self._ctx_ref is context and self._ctx_key == key and self._kv_all is not None:
+        if not new_pass and self._ctx_ref is not None and self._ctx_ref() is context and self._ctx_key == key and self._kv_all is not None:
             tok, self._token = self._token, None     # only the first layer of a pass carries the token
             return self._kv_all, tok
         ctx = context.to(dtype)
@@ -242,7 +248,7 @@ class Attn2Group:
             ctx = ctx.contiguous()
         self._supported = None       # re-validated by the next pass
         kv_all, token = _ProjectAllFn.apply(ctx, self)
-        self._ctx_ref, self._ctx_key = context, key
+        self._ctx_ref, self._ctx_key = weakref.ref(context), key
         self._kv_all = kv_all
         self._token = None
         return kv_all, (token if need_grad else None)

@@ -5,25 +5,29 @@
 // sit in one tile, S and P are RECOMPUTED from Q, K and delta = rowsum(P o dP) is local to a query row, so neither O
 // nor a log-sum-exp is read: HBM traffic is read Q, read dO, write dQ (+ the tiny K, V, dK, dV).
 //
-// One persistent CTA per SM walks a contiguous range of (batch, head, 128-row query tile) items.  352 threads:
-//   warp 0       TMA producer: K|V (double buffered, on a (batch, head) change), Q and dO tiles (3-deep ring)
-//   warp 1       TMEM allocator + MMA issuer (all tcgen05.mma, M128, fp32 accumulate):
-//                  S  = Q  K^T      SS  N80  K64   -> S[g]                    (g = tile parity)
-//                  dP = dO V^T      SS  N80  K64   -> dP[g]
-//                  dQ = dS K        TS  N64  K80   -> dQ      (A = dS, 16-bit, straight from TMEM over dP[g])
-//                  dV^T += dO^T P   SS  M64 N80 K128 -> dKV lanes  0-15 of each quarter   (A = dO, B = P, both MN-major)
-//                  dK^T += Q^T  dS  SS  M64 N80 K128 -> dKV lanes 16-31 of each quarter   (A = Q,  B = dS)
-//                dK / dV are formed TRANSPOSED (rows = head dim, columns = keys): an M64 MMA fetches 2 KB of A + 2.5 KB of B
-//                per K=16 step where the M128 "rows = 128 padded keys" form fetched 4 KB + 2 KB (42 vs 50 cycles per MMA in
-//                isolation, tools/mma_probe.cu; 4 % on the kernel).  An M64 accumulator occupies lanes 0-15 of the four 32-lane quarters,
-//                so the second one interleaves into lanes 16-31 of the same 80 columns.  They accumulate in TMEM across
-//                the CTA's consecutive tiles of one (batch, head).
-//   warps 2..5   softmax group 0 (even tiles), warps 6..9 group 1 (odd tiles); thread = query row = TMEM lane:
-//                P = softmax(S), delta, dS = P o (dP - delta) * scale; P, dS -> shared memory (MN-major, 128B swizzle)
-//                and dS -> TMEM; later dQ TMEM -> 16-bit -> swizzled staging tile; on a (batch, head) change the
-//                group drains dK^T / dV^T (lane = head-dim element, column = key) and adds them to the fp32 accumulators
-//                in global memory (16 consecutive floats per half warp and key).
-//   warp 10      dQ TMA-store issuer (so no softmax thread ever blocks on a store).
+// One persistent CTA per SM walks a contiguous range of (batch, head, 128-row query tile) items.  512 threads in four
+// warpgroups whose register budgets are re-balanced with setmaxnreg (softmax 176, dQ epilogue 96, the rest 56):
+//   WG0  warp 0   TMA producer: K|V (double buffered, on a (batch, head) change), Q and dO tiles (4-deep ring)
+//        warp 1   TMEM allocator + MMA issuer A, per tile t:  dQ(t) = dS K   TS N64 K80  (A = 16-bit dS in TMEM over dP[g])
+//                                                              then S(t+2) = Q K^T, dP(t+2) = dO V^T   SS N80 K64 -> S[g], dP[g]
+//        warp 2   dQ TMA-store issuer
+//        warp 3   MMA issuer B:  dV^T += dO^T P, dK^T += Q^T dS   SS M64 N80 K128 (A = the dO / Q tile read MN-major, B = P / dS);
+//                 released by issuer A only after S / dP(t+2) are in the tensor pipe, so the 16 dV^T / dK^T MMAs of tile t
+//                 never sit in front of the S / dP the next softmax is waiting for
+//   WG1  warps 4-7   softmax group 0 (even tiles)     thread = query row = TMEM lane:
+//   WG2  warps 8-11  softmax group 1 (odd tiles)      P = softmax(S), delta, dS = P o (dP - delta) scale; P, dS -> shared
+//                 memory and dS -> TMEM; on a (batch, head) change the group drains dK^T / dV^T and adds them to the global
+//                 fp32 accumulators (red.global.add.f32, 16 consecutive floats per half warp and key)
+//   WG3  warps 12-15 dQ epilogue: TMEM -> 16-bit -> 128B-swizzled staging tile (then warp 2's TMA store), so a softmax group
+//                 goes straight from dS(t) to S / dP(t+2)
+// Round-2 restructuring (profiles/r2_attn2_bwd_timeline.txt): in round 1 a group's cycle was softmax(t) 2 850 clk -> wait dQ
+// 720 -> dQ epilogue 950 -> wait S / dP(t+2) 720, the last because S / dP(t+2) queued behind dV^T / dK^T(t) in the in-order
+// tensor pipe; issuing S / dP(t+2) first delays dV^T / dK^T(t) and with it the release of tile t's Q / dO slot, which needs the
+// 4th ring slot -- bought by storing P / dS in the un-swizzled ("interleaved") MN-major layout: 8-key x 128-row columns of
+// 16-byte units, 20 KiB each and perfectly coalesced row-per-thread stores, instead of two 64-key 128B-swizzle slabs (32 KiB).
+// dK / dV are formed TRANSPOSED (rows = head dim, columns = keys): an M64 MMA fetches 2 KB of A + 2.5 KB of B per K=16 step;
+// an M64 accumulator occupies lanes 0-15 of each 32-lane quarter, so dK^T interleaves into lanes 16-31 of dV^T's 80 columns.
+// They accumulate in TMEM across the CTA's consecutive tiles of one (batch, head).
 // TMEM (512 columns): S[2] | dP[2] (160 each pair), dQ 64, dV^T / dK^T 80 (lane-interleaved).
 // Algorithmic bytes per tile: 2 x 16 KiB in (Q, dO) + 16 KiB out (dQ); FLOPs 10 x 128 x 80 x 64.
 #include "tc05.cuh"
@@ -32,25 +36,23 @@ namespace pea {
 namespace {
 
 constexpr int kQT = 128, kD = 64, kLP = 80;
-constexpr int kRing = 3;
-#ifdef PEA_BWD_SPLIT
-constexpr int kThreads = 384;   // + warp 11: the S / dP issuer
-#else
-constexpr int kThreads = 352;
-#endif
-constexpr int kSdpWarp = 11;
+constexpr int kRing = 4;
+constexpr int kThreads = 512;
+constexpr int kRegsSoftmax = 176, kRegsEpilogue = 96, kRegsOther = 56;   // 128 * 56 + 256 * 176 + 128 * 96 <= 65 536
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kTS = 0, kTdP = 80, kTPair = 160, kTdQ = 320, kTdKV = 384;
 constexpr uint32_t kLaneDK = 16u << 16;        // dK^T sits 16 lanes below dV^T in every quarter
 constexpr uint32_t kTile = kQT * kD * 2;        // 16 KiB: one Q / dO / dQ tile
 constexpr uint32_t kKV = kLP * kD * 2;          // 10 KiB: K or V
-constexpr uint32_t kSlab = kQT * 128;           // 16 KiB: [128 q][64 keys] slab of P / dS
+constexpr uint32_t kPCol = kQT * 16;            // 2 KiB: one 8-key column of P / dS ([128 q][8 keys], 16 B per row)
+constexpr uint32_t kPBytes = (kLP / 8) * kPCol; // 20 KiB
 constexpr uint32_t kOffKV = 0;                              // 2 x (K | V)
-constexpr uint32_t kOffRing = 2 * 2 * kKV;                  // 3 x (Q | dO)
-constexpr uint32_t kOffP = kOffRing + kRing * 2 * kTile;    // 2 slabs
-constexpr uint32_t kOffdS = kOffP + 2 * kSlab;              // 2 slabs
-constexpr uint32_t kOffStage = kOffdS + 2 * kSlab;          // dQ staging
-constexpr uint32_t kSmemBytes = kOffStage + kTile + 1024;
+constexpr uint32_t kOffRing = 2 * 2 * kKV;                  // 4 x (Q | dO)
+constexpr uint32_t kOffP = kOffRing + kRing * 2 * kTile;
+constexpr uint32_t kOffdS = kOffP + kPBytes;
+constexpr uint32_t kOffStage = kOffdS + kPBytes;            // dQ staging
+constexpr uint32_t kSmemBytes = kOffStage + kTile + 1024;   // 225 KiB
+static_assert(kSmemBytes + 512 <= 227 * 1024, "shared memory budget");
 
 struct BwdParams {
   CUtensorMap tmQ, tmdO, tmKV, tmdQ;
@@ -74,9 +76,11 @@ __device__ __forceinline__ float ex2(float x) {
 __device__ __forceinline__ void st_shared16(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
+template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 
-// Optional per-tile event timeline of CTA 0 (build with -DPEA_TRACE, read with tools/trace_bwd.py): how the round-1
-// bottleneck analysis in DESIGN.md section 4.2 was obtained.  Expands to nothing in the product build.
+// Optional per-tile event timeline of CTA 0 (build with -DPEA_TRACE, read with tools/trace_bwd.py).  Expands to nothing in
+// the product build.
 #ifdef PEA_TRACE
 __device__ unsigned long long g_trace[16 * 64 * 16];   // [role][tile][event]
 #define TRACE(role, tile, ev) do { if (blockIdx.x == 0 && (tile) < 64 && lane == 0) g_trace[((role) * 64 + (tile)) * 16 + (ev)] = clock64(); } while (0)
@@ -88,8 +92,7 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads, 1) attn2_bwd_tc_kernel(const __grid_constant__ BwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t kv_full[2], kv_empty[2], ring_full[kRing], ring_empty[kRing];
-  __shared__ __align__(8) uint64_t sdp_full[2], ds_ready[2], pds_free, dq_full, dq_free, dkv_full, dkv_free, dq_staged, stage_free;
-  __shared__ __align__(8) uint64_t dq_done[2];   // per group: dQ(t) has consumed dS from dP[g] -> S / dP(t+2) may overwrite S[g], dP[g]
+  __shared__ __align__(8) uint64_t sdp_full[2], ds_ready[2], pds_free, dq_full, dq_free, dkv_full, dkv_free, dq_staged, stage_free, go_dkv;
   __shared__ uint32_t tmem_slot;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -97,22 +100,20 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_bwd_tc_kernel(const __grid_
   const int item0 = blockIdx.x * p.tiles_per_cta;
   const int ntiles = min(p.tiles_per_cta, p.total_tiles - item0);
   const int tpb = p.tiles_per_bh;
-  // Work items are consecutive: every role walks (batch, head, tile) with counters, and these are the kernel's only integer
-  // divisions (the MMA warp is one latency-bound instruction stream; see attn2_tc.cu).
-  const int bh0 = item0 / tpb, rem0 = item0 - bh0 * tpb;
-  const int b0 = bh0 / p.H, h0 = bh0 - b0 * p.H;
+  // Work items are consecutive: every role walks (batch, head, tile) with counters; the only divisions of the kernel are these
+  const int bh0 = fast_div(item0, tpb), rem0 = item0 - bh0 * tpb;
+  const int b0 = fast_div(bh0, p.H), h0 = bh0 - b0 * p.H;
   if (warp == 0) TRACE(0, 63, 15);   // kernel entry
 
   if (warp == 0 && lane == 0) {
     tc::prefetch_tmap(&p.tmQ); tc::prefetch_tmap(&p.tmdO); tc::prefetch_tmap(&p.tmKV); tc::prefetch_tmap(&p.tmdQ);
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
-      tc::mbar_init(smem_u32(&kv_full[i]), 1); tc::mbar_init(smem_u32(&kv_empty[i]), 1);
+      tc::mbar_init(smem_u32(&kv_full[i]), 1); tc::mbar_init(smem_u32(&kv_empty[i]), 2);   // freed by BOTH MMA issuers
       tc::mbar_init(smem_u32(&sdp_full[i]), 1); tc::mbar_init(smem_u32(&ds_ready[i]), 4);
     }
 #pragma unroll
     for (int i = 0; i < kRing; ++i) { tc::mbar_init(smem_u32(&ring_full[i]), 1); tc::mbar_init(smem_u32(&ring_empty[i]), 1); }
-    tc::mbar_init(smem_u32(&dq_done[0]), 1); tc::mbar_init(smem_u32(&dq_done[1]), 1);
     tc::mbar_init(smem_u32(&pds_free), 1);
     tc::mbar_init(smem_u32(&dq_full), 1);
     tc::mbar_init(smem_u32(&dq_free), 4);
@@ -120,6 +121,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_bwd_tc_kernel(const __grid_
     tc::mbar_init(smem_u32(&dkv_free), 4);
     tc::mbar_init(smem_u32(&dq_staged), 4);
     tc::mbar_init(smem_u32(&stage_free), 1);
+    tc::mbar_init(smem_u32(&go_dkv), 1);
     tc::fence_mbar_init();
   }
   if (warp == 1) tc::tmem_alloc(smem_u32(&tmem_slot), kTmemCols);
@@ -130,149 +132,168 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_bwd_tc_kernel(const __grid_
   pdl_wait();                 // see attn2_tc.cu: the prologue overlapped the preceding kernel's tail under PEA_LAUNCH_PDL
   pdl_launch_dependents();
 
-  if (warp == 0) {
-    // ===== TMA producer =====
-    int kv_n = 0, s = 0;
-    uint32_t ring_ph = 0;
-    int b = b0, h = h0, tile = rem0;
-    for (int t = 0; t < ntiles; ++t) {
-      if (t == 0 || tile == 0) {   // first tile of a (batch, head) in this CTA's range
-        const int kb = kv_n & 1;
-        tc::mbar_wait(smem_u32(&kv_empty[kb]), ((uint32_t)(kv_n >> 1) & 1u) ^ 1u);
+  // K-major tiles [rows][64 x 16-bit] (Q, dO as A; K, V as B of S / dP): K=16 step = 32 B inside the 128B swizzle atom.
+  // MN-major 128B-swizzle tiles: K as B of dQ, Q / dO as A of dK^T / dV^T ([k rows][64 contiguous]): K=16 step = 16 rows = 2048 B.
+  // MN-major un-swizzled ("interleaved") P / dS as B of dV^T / dK^T: core matrix = 8 q-rows x 8 keys = 128 contiguous bytes;
+  //   next 8 keys (SBO) 2 KiB further, next 8 q-rows (LBO) 128 B further; K=16 step = 2 core matrices = 256 B.
+  constexpr uint64_t kDescK = ((uint64_t)1 << 16) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
+  constexpr uint64_t kDescMN = ((uint64_t)1 << 16) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
+  constexpr uint64_t kDescPdS = ((uint64_t)(128u >> 4) << 16) | ((uint64_t)(kPCol >> 4) << 32) | (1ull << 46);
+
+  if (warp < 4) {
+    reg_dec<kRegsOther>();
+    if (warp == 0) {
+      // ===== TMA producer =====
+      int kv_n = 0, s = 0;
+      uint32_t ring_ph = 0;
+      int b = b0, h = h0, tile = rem0;
+      for (int t = 0; t < ntiles; ++t) {
+        if (t == 0 || tile == 0) {   // first tile of a (batch, head) in this CTA's range
+          const int kb = kv_n & 1;
+          tc::mbar_wait(smem_u32(&kv_empty[kb]), ((uint32_t)(kv_n >> 1) & 1u) ^ 1u);
+          if (tc::elect_one()) {
+            const uint32_t bk = smem_u32(&kv_full[kb]);
+            tc::mbar_expect_tx(bk, 2 * kKV);
+            tc::tma_load_3d(smem + kOffKV + kb * 2 * kKV, &p.tmKV, bk, h * kD, 0, b);
+            tc::tma_load_3d(smem + kOffKV + kb * 2 * kKV + kKV, &p.tmKV, bk, p.voff + h * kD, 0, b);
+          }
+          __syncwarp();
+          ++kv_n;
+        }
+        tc::mbar_wait(smem_u32(&ring_empty[s]), ring_ph ^ 1u);
+        TRACE(0, t, 0);
         if (tc::elect_one()) {
-          const uint32_t bk = smem_u32(&kv_full[kb]);
-          tc::mbar_expect_tx(bk, 2 * kKV);
-          tc::tma_load_3d(smem + kOffKV + kb * 2 * kKV, &p.tmKV, bk, h * kD, 0, b);
-          tc::tma_load_3d(smem + kOffKV + kb * 2 * kKV + kKV, &p.tmKV, bk, p.voff + h * kD, 0, b);
+          const uint32_t fb = smem_u32(&ring_full[s]);
+          tc::mbar_expect_tx(fb, 2 * kTile);
+          tc::tma_load_3d(smem + kOffRing + s * 2 * kTile, &p.tmQ, fb, h * kD, tile * kQT, b);
+          tc::tma_load_3d(smem + kOffRing + s * 2 * kTile + kTile, &p.tmdO, fb, h * kD, tile * kQT, b);
         }
         __syncwarp();
-        ++kv_n;
+        if (++s == kRing) { s = 0; ring_ph ^= 1u; }
+        if (++tile == tpb) { tile = 0; if (++h == p.H) { h = 0; ++b; } }
       }
-      tc::mbar_wait(smem_u32(&ring_empty[s]), ring_ph ^ 1u);
-      TRACE(0, t, 0);
-      if (tc::elect_one()) {
-        const uint32_t fb = smem_u32(&ring_full[s]);
-        tc::mbar_expect_tx(fb, 2 * kTile);
-        tc::tma_load_3d(smem + kOffRing + s * 2 * kTile, &p.tmQ, fb, h * kD, tile * kQT, b);
-        tc::tma_load_3d(smem + kOffRing + s * 2 * kTile + kTile, &p.tmdO, fb, h * kD, tile * kQT, b);
-      }
-      __syncwarp();
-      if (++s == kRing) { s = 0; ring_ph ^= 1u; }
-      if (++tile == tpb) { tile = 0; if (++h == p.H) { h = 0; ++b; } }
-    }
-  } else if (warp == 1 || warp == kSdpWarp) {
-    // ===== MMA issuers.  PEA_BWD_SPLIT: warp 1 issues dQ / dV^T / dK^T, warp 11 issues S / dP -- S / dP(t+2) then starts the
-    // moment dQ(t) has consumed dS (dq_done[g]) instead of queueing behind the 16 dV^T / dK^T MMAs of tile t in one
-    // in-order instruction stream, which put ~1 300 cycles on the critical path of every softmax group
-    // (profiles/r1_attn2_bwd_timeline.txt: sdp_full(t) -> softmax 2 800 -> dQ, dV^T, dK^T 1 300 -> S, dP 1 280 -> sdp_full(t+2)). =====
-    // K-major tiles [rows][64 x 16-bit] (Q, dO as A; K, V as B of S / dP): K=16 step = 32 B inside the swizzle atom.
-    // MN-major tiles: K, Q, dO as B ([k rows][64 contiguous]): K=16 step = 16 rows = 2048 B;
-    //                 P, dS as A ([q rows][keys], two 64-key slabs 16 KiB apart = LBO): K=16 step = 16 q rows = 2048 B.
-    constexpr uint64_t kDescK = ((uint64_t)1 << 16) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
-    constexpr uint64_t kDescMN = ((uint64_t)(kSlab >> 4) << 16) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
-    int s_pos = rem0, s_kvn = 0;   // tile-in-head position / K|V bookkeeping of the S/dP stream (runs up to two tiles ahead)
-    int m_pos = rem0, m_kvn = 0;   // ... and of the dQ/dK/dV stream
-    int s_rs = 0, m_rs = 0;        // ring slot (t % kRing) of either stream, as counters
-    uint32_t s_rph = 0;            // (t / kRing) & 1 of the S/dP stream
-    int flushes = 0;
-    auto issue_sdp = [&](int t) {
-      if (t == 0 || s_pos == 0) {
-        tc::mbar_wait(smem_u32(&kv_full[s_kvn & 1]), (uint32_t)(s_kvn >> 1) & 1u);
-        ++s_kvn;
-      }
-      if (++s_pos == tpb) s_pos = 0;
-      const int kb = (s_kvn - 1) & 1, rs = s_rs, g = t & 1;
-      const uint32_t rph = s_rph;
-      if (++s_rs == kRing) { s_rs = 0; s_rph ^= 1u; }
-      TRACE(1, t, 0);
-      tc::mbar_wait(smem_u32(&ring_full[rs]), rph);
-      TRACE(1, t, 1);
-      tc::fence_after_sync();
-      if (tc::elect_one()) {
-        const uint32_t qa = (smem + kOffRing + rs * 2 * kTile) >> 4, doa = qa + (kTile >> 4);
-        const uint32_t ka = (smem + kOffKV + kb * 2 * kKV) >> 4, va = ka + (kKV >> 4);
-        const uint32_t ts = tmem + g * kTPair + kTS, tdp = tmem + g * kTPair + kTdP;
-        // The K steps of one accumulator form a dependent chain that the tensor pipe runs at ~105 clk per step for these
-        // small N (latency, not math: 40-50 clk); two independent accumulators interleaved overlap their latencies.
-#pragma unroll
-        for (int k = 0; k < kD / 16; ++k) {
-          tc::mma_f16_ss(ts, kDescK | (uint64_t)(qa + k * 2), kDescK | (uint64_t)(ka + k * 2), p.idesc_s, k > 0);
-          tc::mma_f16_ss(tdp, kDescK | (uint64_t)(doa + k * 2), kDescK | (uint64_t)(va + k * 2), p.idesc_s, k > 0);
+    } else if (warp == 1) {
+      // ===== MMA issuer A: dQ(t), then S / dP(t+2) =====
+      int s_pos = rem0, s_kvn = 0;   // tile-in-head position / K|V bookkeeping of the S / dP stream (two tiles ahead)
+      int m_pos = rem0, m_kvn = 0;   // ... and of the dQ stream
+      int s_rs = 0;                  // ring slot (t % kRing) of the S / dP stream
+      uint32_t s_rph = 0;            // (t / kRing) & 1
+      auto issue_sdp = [&](int t) {
+        if (t == 0 || s_pos == 0) {
+          tc::mbar_wait(smem_u32(&kv_full[s_kvn & 1]), (uint32_t)(s_kvn >> 1) & 1u);
+          ++s_kvn;
         }
-        tc::mma_commit(smem_u32(&sdp_full[g]));
-      }
-      __syncwarp();
-    };
-#ifdef PEA_BWD_SPLIT
-    if (warp == kSdpWarp) {
+        if (++s_pos == tpb) s_pos = 0;
+        const int kb = (s_kvn - 1) & 1, rs = s_rs, g = t & 1;
+        const uint32_t rph = s_rph;
+        if (++s_rs == kRing) { s_rs = 0; s_rph ^= 1u; }
+        TRACE(1, t, 0);
+        tc::mbar_wait(smem_u32(&ring_full[rs]), rph);
+        TRACE(1, t, 1);
+        tc::fence_after_sync();
+        if (tc::elect_one()) {
+          const uint32_t qa = (smem + kOffRing + rs * 2 * kTile) >> 4, doa = qa + (kTile >> 4);
+          const uint32_t ka = (smem + kOffKV + kb * 2 * kKV) >> 4, va = ka + (kKV >> 4);
+          const uint32_t ts = tmem + g * kTPair + kTS, tdp = tmem + g * kTPair + kTdP;
+#pragma unroll
+          for (int k = 0; k < kD / 16; ++k) {
+            tc::mma_f16_ss(ts, kDescK | (uint64_t)(qa + k * 2), kDescK | (uint64_t)(ka + k * 2), p.idesc_s, k > 0);
+            tc::mma_f16_ss(tdp, kDescK | (uint64_t)(doa + k * 2), kDescK | (uint64_t)(va + k * 2), p.idesc_s, k > 0);
+          }
+          tc::mma_commit(smem_u32(&sdp_full[g]));
+        }
+        __syncwarp();
+      };
+      if (ntiles > 0) issue_sdp(0);
+      if (ntiles > 1) issue_sdp(1);
       for (int t = 0; t < ntiles; ++t) {
-        if (t >= 2) tc::mbar_wait(smem_u32(&dq_done[t & 1]), (uint32_t)((t >> 1) - 1) & 1u);   // dQ(t-2) done with dP[g]
-        issue_sdp(t);
-      }
-    } else
-#else
-    if (ntiles > 0) issue_sdp(0);
-    if (ntiles > 1) issue_sdp(1);
-#endif
-    for (int t = 0; t < ntiles; ++t) {
-      const int g = t & 1, rs = m_rs;
-      if (++m_rs == kRing) m_rs = 0;
-      const bool first_of_bh = t == 0 || m_pos == 0;
-      if (first_of_bh) ++m_kvn;
-      const int kb = (m_kvn - 1) & 1;
-      const bool last_tile = t + 1 == ntiles;
-      const bool last_of_bh = !last_tile && (m_pos == tpb - 1);
-      if (++m_pos == tpb) m_pos = 0;
-      TRACE(1, t, 2);
-      tc::mbar_wait(smem_u32(&ds_ready[g]), (uint32_t)(t >> 1) & 1u);
-      TRACE(1, t, 3);
-      if (t > 0) tc::mbar_wait(smem_u32(&dq_free), (uint32_t)(t - 1) & 1u);            // dQ TMEM drained by tile t-1's epilogue
-      TRACE(1, t, 4);
-      if (first_of_bh && flushes > 0) tc::mbar_wait(smem_u32(&dkv_free), (uint32_t)(flushes - 1) & 1u);  // dK/dV TMEM drained
-      tc::fence_after_sync();
-      if (tc::elect_one()) {
-        const uint32_t qa = (smem + kOffRing + rs * 2 * kTile) >> 4, doa = qa + (kTile >> 4);
-        const uint32_t ka = (smem + kOffKV + kb * 2 * kKV) >> 4;
-        const uint32_t pa = (smem + kOffP) >> 4, dsa = (smem + kOffdS) >> 4;
-        const uint32_t tds = tmem + g * kTPair + kTdP;
-        // dQ = dS K   (A: 16-bit dS in TMEM, 8 columns per K=16 step; B: K tile read MN-major)
+        const int g = t & 1;
+        if (t == 0 || m_pos == 0) ++m_kvn;
+        const int kb = (m_kvn - 1) & 1;
+        const bool last_of_bh = (t + 1 < ntiles) && (m_pos == tpb - 1);
+        if (++m_pos == tpb) m_pos = 0;
+        TRACE(1, t, 2);
+        tc::mbar_wait(smem_u32(&ds_ready[g]), (uint32_t)(t >> 1) & 1u);
+        TRACE(1, t, 3);
+        if (t > 0) tc::mbar_wait(smem_u32(&dq_free), (uint32_t)(t - 1) & 1u);   // dQ TMEM drained by the epilogue warpgroup
+        TRACE(1, t, 4);
+        tc::fence_after_sync();
+        if (tc::elect_one()) {
+          const uint32_t ka = (smem + kOffKV + kb * 2 * kKV) >> 4;
+          const uint32_t tds = tmem + g * kTPair + kTdP;
+          // dQ = dS K   (A: 16-bit dS in TMEM, 8 columns per K=16 step; B: K tile read MN-major)
 #pragma unroll
-        for (int k = 0; k < kLP / 16; ++k)
-          tc::mma_f16_ts(tmem + kTdQ, tds + k * 8, kDescMN | (uint64_t)(ka + k * 128), p.idesc_dq, k > 0);
-        tc::mma_commit(smem_u32(&dq_full));
-#ifdef PEA_BWD_SPLIT
-        tc::mma_commit(smem_u32(&dq_done[g]));
-#endif
-        // dV^T += dO^T P ; dK^T += Q^T dS   (reduction over the 128 query rows; the two chains interleaved)
-#pragma unroll
-        for (int k = 0; k < kQT / 16; ++k) {
-          tc::mma_f16_ss(tmem + kTdKV, kDescMN | (uint64_t)(doa + k * 128), kDescMN | (uint64_t)(pa + k * 128), p.idesc_dkv,
-                         (k > 0) ? 1u : (uint32_t)!first_of_bh);
-          tc::mma_f16_ss(tmem + kTdKV + kLaneDK, kDescMN | (uint64_t)(qa + k * 128), kDescMN | (uint64_t)(dsa + k * 128), p.idesc_dkv,
-                         (k > 0) ? 1u : (uint32_t)!first_of_bh);
+          for (int k = 0; k < kLP / 16; ++k)
+            tc::mma_f16_ts(tmem + kTdQ, tds + k * 8, kDescMN | (uint64_t)(ka + k * 128), p.idesc_dq, k > 0);
+          tc::mma_commit(smem_u32(&dq_full));
+          if (last_of_bh) tc::mma_commit(smem_u32(&kv_empty[kb]));   // (1 of 2) this issuer's last read of the K|V buffer
         }
-        tc::mma_commit(smem_u32(&pds_free));            // P / dS shared-memory tiles reusable
-        tc::mma_commit(smem_u32(&ring_empty[rs]));      // Q / dO slot reusable
-        if (last_of_bh || last_tile) tc::mma_commit(smem_u32(&dkv_full));
-        if (last_of_bh) tc::mma_commit(smem_u32(&kv_empty[kb]));
+        __syncwarp();
+        if (t + 2 < ntiles) issue_sdp(t + 2);     // same thread, after dQ(t): the pipe runs them in this order (dS before dP(t+2))
+        if (lane == 0) tc::mbar_arrive(smem_u32(&go_dkv));   // issuer B may now queue dV^T / dK^T(t) behind them
       }
-      __syncwarp();
-      if (last_of_bh || last_tile) ++flushes;
-#ifndef PEA_BWD_SPLIT
-      if (t + 2 < ntiles) issue_sdp(t + 2);
-#endif
+    } else if (warp == 3) {
+      // ===== MMA issuer B: dV^T += dO^T P ; dK^T += Q^T dS (reduction over the 128 query rows; the two chains interleaved) =====
+      int m_pos = rem0, m_kvn = 0, m_rs = 0, flushes = 0;
+      for (int t = 0; t < ntiles; ++t) {
+        const int g = t & 1, rs = m_rs;
+        if (++m_rs == kRing) m_rs = 0;
+        const bool first_of_bh = t == 0 || m_pos == 0;
+        if (first_of_bh) ++m_kvn;
+        const int kb = (m_kvn - 1) & 1;
+        const bool last_tile = t + 1 == ntiles;
+        const bool last_of_bh = !last_tile && (m_pos == tpb - 1);
+        if (++m_pos == tpb) m_pos = 0;
+        tc::mbar_wait(smem_u32(&ds_ready[g]), (uint32_t)(t >> 1) & 1u);        // P / dS of tile t are in shared memory
+        tc::mbar_wait(smem_u32(&go_dkv), (uint32_t)t & 1u);
+        if (first_of_bh && flushes > 0) tc::mbar_wait(smem_u32(&dkv_free), (uint32_t)(flushes - 1) & 1u);  // dK/dV TMEM drained
+        tc::fence_after_sync();
+        if (tc::elect_one()) {
+          const uint32_t qa = (smem + kOffRing + rs * 2 * kTile) >> 4, doa = qa + (kTile >> 4);
+          const uint32_t pa = (smem + kOffP) >> 4, dsa = (smem + kOffdS) >> 4;
+#pragma unroll
+          for (int k = 0; k < kQT / 16; ++k) {
+            tc::mma_f16_ss(tmem + kTdKV, kDescMN | (uint64_t)(doa + k * 128), kDescPdS | (uint64_t)(pa + k * 16), p.idesc_dkv,
+                           (k > 0) ? 1u : (uint32_t)!first_of_bh);
+            tc::mma_f16_ss(tmem + kTdKV + kLaneDK, kDescMN | (uint64_t)(qa + k * 128), kDescPdS | (uint64_t)(dsa + k * 16), p.idesc_dkv,
+                           (k > 0) ? 1u : (uint32_t)!first_of_bh);
+          }
+          tc::mma_commit(smem_u32(&pds_free));            // P / dS shared-memory tiles reusable
+          tc::mma_commit(smem_u32(&ring_empty[rs]));      // Q / dO slot reusable
+          if (last_of_bh || last_tile) tc::mma_commit(smem_u32(&dkv_full));
+          if (last_of_bh) tc::mma_commit(smem_u32(&kv_empty[kb]));   // (2 of 2)
+        }
+        __syncwarp();
+        if (last_of_bh || last_tile) ++flushes;
+      }
+    } else {
+      // ===== warp 2: dQ TMA-store issuer =====
+      int b = b0, h = h0, tile = rem0;
+      for (int t = 0; t < ntiles; ++t) {
+        tc::mbar_wait(smem_u32(&dq_staged), (uint32_t)t & 1u);
+        if (tc::elect_one()) {
+          tc::tma_store_3d(&p.tmdQ, smem + kOffStage, h * kD, tile * kQT, b);
+          tc::tma_store_commit();
+          tc::tma_store_wait_read<0>();
+          tc::mbar_arrive(smem_u32(&stage_free));
+          // (the global writes of the last store complete by grid end; shared memory only has to outlive the READ)
+        }
+        __syncwarp();
+        if (++tile == tpb) { tile = 0; if (++h == p.H) { h = 0; ++b; } }
+      }
     }
-  } else if (warp < 10) {
-    // ===== softmax / epilogue groups =====
-    const int g = (warp - 2) >> 2;
+  } else if (warp < 12) {
+    // ===== softmax groups =====
+    reg_inc<kRegsSoftmax>();
+    const int g = (warp - 4) >> 2;
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     const uint32_t t_s = tmem + g * kTPair + kTS + lane_off, t_dp = tmem + g * kTPair + kTdP + lane_off;
-    const uint32_t row_off = (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u;
+    const uint32_t row_off = (uint32_t)row * 16u;       // this row's 16-byte unit inside every 8-key column of P / dS
     const int L = p.L;
     const float sl2 = p.scale_log2, scale = p.scale;
-    int flushes = 0;   // counted identically in both groups and the MMA warp
+    int flushes = 0;   // counted identically in both groups and MMA issuer B
     int nb = b0, nh = h0, pos = rem0;   // (batch, head, tile-in-head) of tile t, advanced once per tile
     for (int t = 0; t < ntiles; ++t) {
       const int b = nb, h = nh;
@@ -362,14 +383,13 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_bwd_tc_kernel(const __grid_
         tmem_st8(t_dp + c * 8, d8);
       }
 
-      // ---- P / dS shared-memory tiles free?  (dK/dV MMAs of the previous tile have read them) -- only the stores wait
+      // ---- P / dS shared-memory tiles free?  (dV^T / dK^T of the previous tile have read them) -- only the stores wait
       TRACE(2 + g, t, 2);
       if (t > 0) tc::mbar_wait(smem_u32(&pds_free), (uint32_t)(t - 1) & 1u);
       TRACE(2 + g, t, 3);
 #pragma unroll
-      for (int chunk = 0; chunk < kLP / 8; ++chunk) {          // 8 keys = 16 bytes; MN-major, 128B swizzle
-        const uint32_t slab = (uint32_t)(chunk >> 3) * kSlab;
-        const uint32_t o = slab + row_off + (uint32_t)(((chunk & 7) ^ (row & 7)) << 4);
+      for (int chunk = 0; chunk < kLP / 8; ++chunk) {          // 8 keys = 16 bytes; un-swizzled MN-major: [8-key column][q row]
+        const uint32_t o = (uint32_t)chunk * kPCol + row_off;  // a warp writes 512 contiguous bytes per store
         st_shared16(smem + kOffP + o, pp[chunk * 4 + 0], pp[chunk * 4 + 1], pp[chunk * 4 + 2], pp[chunk * 4 + 3]);
         st_shared16(smem + kOffdS + o, dd[chunk * 4 + 0], dd[chunk * 4 + 1], dd[chunk * 4 + 2], dd[chunk * 4 + 3]);
       }
@@ -379,34 +399,6 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_bwd_tc_kernel(const __grid_
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(smem_u32(&ds_ready[g]));
       TRACE(2 + g, t, 4);
-
-      // ---- dQ epilogue: TMEM -> 16-bit -> swizzled staging tile -> (warp 10) TMA store -------------------------------
-      tc::mbar_wait(smem_u32(&dq_full), (uint32_t)t & 1u);
-      TRACE(2 + g, t, 5);
-      if (t > 0) tc::mbar_wait(smem_u32(&stage_free), (uint32_t)(t - 1) & 1u);   // previous store has read the staging tile
-      TRACE(2 + g, t, 6);
-      tc::fence_after_sync();
-      {
-        uint32_t ov[64];
-        uint32_t(&o0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&ov[0]);
-        uint32_t(&o1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&ov[32]);
-        tc::tmem_ld32(tmem + kTdQ + lane_off, o0);
-        tc::tmem_ld32(tmem + kTdQ + lane_off + 32, o1);
-        tc::tmem_ld_wait();
-#pragma unroll
-        for (int chunk = 0; chunk < 8; ++chunk) {
-          const uint32_t addr = smem + kOffStage + (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4);
-          st_shared16(addr, pack2<T>(__uint_as_float(ov[chunk * 8 + 0]), __uint_as_float(ov[chunk * 8 + 1])),
-                      pack2<T>(__uint_as_float(ov[chunk * 8 + 2]), __uint_as_float(ov[chunk * 8 + 3])),
-                      pack2<T>(__uint_as_float(ov[chunk * 8 + 4]), __uint_as_float(ov[chunk * 8 + 5])),
-                      pack2<T>(__uint_as_float(ov[chunk * 8 + 6]), __uint_as_float(ov[chunk * 8 + 7])));
-        }
-      }
-      tc::fence_before_sync();
-      tc::fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) { tc::mbar_arrive(smem_u32(&dq_free)); tc::mbar_arrive(smem_u32(&dq_staged)); }
-      TRACE(2 + g, t, 7);
 
       // ---- (batch, head) boundary: drain dV^T | dK^T (lane = head-dim element) into the global fp32 accumulators -----
       if (flush) {
@@ -440,26 +432,41 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_bwd_tc_kernel(const __grid_
         ++flushes;
       }
     }
-  } else if (warp == 10) {
-    // ===== warp 10: dQ TMA-store issuer =====
-    int b = b0, h = h0, tile = rem0;
+    TRACE(2 + g, 63, 14);   // group done (incl. dK/dV flush)
+  } else {
+    // ===== warps 12-15: dQ epilogue: TMEM -> 16-bit -> swizzled staging tile -> (warp 2) TMA store =====
+    reg_dec<kRegsEpilogue>();
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     for (int t = 0; t < ntiles; ++t) {
-      tc::mbar_wait(smem_u32(&dq_staged), (uint32_t)t & 1u);
-      if (tc::elect_one()) {
-        tc::tma_store_3d(&p.tmdQ, smem + kOffStage, h * kD, tile * kQT, b);
-        tc::tma_store_commit();
-        tc::tma_store_wait_read<0>();
-        tc::mbar_arrive(smem_u32(&stage_free));
-#ifndef PEA_EXP_WAITREAD
-        if (t + 1 == ntiles) tc::tma_store_wait<0>();   // (the global writes complete by grid end in any case)
-#endif
-      }
+      tc::mbar_wait(smem_u32(&dq_full), (uint32_t)t & 1u);
+      tc::fence_after_sync();
+      uint32_t ov[64];
+      uint32_t(&o0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&ov[0]);
+      uint32_t(&o1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&ov[32]);
+      tc::tmem_ld32(tmem + kTdQ + lane_off, o0);
+      tc::tmem_ld32(tmem + kTdQ + lane_off + 32, o1);
+      tc::tmem_ld_wait();
+      tc::fence_before_sync();
       __syncwarp();
-      if (++tile == tpb) { tile = 0; if (++h == p.H) { h = 0; ++b; } }
+      if (lane == 0) tc::mbar_arrive(smem_u32(&dq_free));      // dQ TMEM may be overwritten by tile t + 1
+      if (t > 0) tc::mbar_wait(smem_u32(&stage_free), (uint32_t)(t - 1) & 1u);   // previous store has read the staging tile
+#pragma unroll
+      for (int chunk = 0; chunk < 8; ++chunk) {
+        const uint32_t addr = smem + kOffStage + (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4);
+        st_shared16(addr, pack2<T>(__uint_as_float(ov[chunk * 8 + 0]), __uint_as_float(ov[chunk * 8 + 1])),
+                    pack2<T>(__uint_as_float(ov[chunk * 8 + 2]), __uint_as_float(ov[chunk * 8 + 3])),
+                    pack2<T>(__uint_as_float(ov[chunk * 8 + 4]), __uint_as_float(ov[chunk * 8 + 5])),
+                    pack2<T>(__uint_as_float(ov[chunk * 8 + 6]), __uint_as_float(ov[chunk * 8 + 7])));
+      }
+      tc::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(smem_u32(&dq_staged));
+      TRACE(4, t, 0);
     }
   }
 
-  if (warp >= 2 && warp < 10) TRACE(2 + ((warp - 2) >> 2), 63, 14);   // group done (incl. dK/dV flush)
   tc::fence_before_sync();
   __syncthreads();
   if (warp == 0) TRACE(0, 63, 14);   // all roles done

@@ -112,8 +112,8 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_fwd_tc_kernel(const __grid_
   // Work items are consecutive, so every role walks (batch, head, tile) with counters; the only integer divisions of the
   // kernel are these.  (The MMA warp is a single latency-bound instruction stream that shares its scheduler with three
   // softmax warps: four divisions per tile in it were a third of the tile period.)
-  const int bh0 = item0 / tpb, rem0 = item0 - bh0 * tpb;
-  const int b0 = bh0 / p.H, h0 = bh0 - b0 * p.H;
+  const int bh0 = fast_div(item0, tpb), rem0 = item0 - bh0 * tpb;
+  const int b0 = fast_div(bh0, p.H), h0 = bh0 - b0 * p.H;
 
 #ifdef PEA_EXP_PARINIT
   if (warp == 0) {

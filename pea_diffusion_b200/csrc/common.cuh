@@ -130,6 +130,15 @@ __device__ __forceinline__ float gelu_exact_grad(float x) {
   return cdf + x * pdf;
 }
 
+// n / d for 0 <= n < 2^23, d >= 1 without the ~300-cycle emulated integer division: float quotient, then exact fix-up.
+// (Two of these at kernel entry replaced ~650 cycles of every warp's prologue in the attention kernels.)
+__device__ __forceinline__ int fast_div(int n, int d) {
+  int q = __float2int_rz(__fdividef((float)n, (float)d));
+  q -= (q * d > n);
+  q += ((q + 1) * d <= n);
+  return q;
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
 // streaming 128-bit global accesses (read-once / write-once data: keep it out of L1)
