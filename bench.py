@@ -17,7 +17,8 @@ One JSON line on stdout (rank 0):
   roofline       the fused attn2 forward+backward kernels: algorithmic bytes / CUDA-event time of
                  every launch inside a replayed CUDA graph of the step, against MEASURED_PEAKS.json; plus
                  .per_kernel        every kernel family of the library inside the step
-                 .in_step_marginal  bracket-free: (replayed step) - (the same step captured without the attention launches)
+                 .in_chain_marginal bracket-free: graph of 20 x [to_q GEMM -> attn2 -> to_out GEMM] minus the same graph without
+                                    the attention launches, for the step's two shapes and both directions
                  .sweep             BASELINE.json configs[3]: the config-4 attn2 sweep (B=8; N 1024/4096/16384; C 640/1280;
                                     L 77, and 52 / 64 once), each launch alone, L2 flushed -- metric M2
   strong         configs[2]: the same step at GLOBAL batch 64 (64/W per rank, micro-batches of 8), samples/s
@@ -320,23 +321,62 @@ def time_replays(g, n):
     return ts[len(ts) // 2]
 
 
-def in_step_marginal(trainer, replays=5):
-    """Bracket-free cost of the attention launches inside the step: median replay time of the captured forward+backward
-    minus the same graph captured with ops.SKIP_ATTN2 (outputs allocated, nothing launched).  Serial schedule (no teacher
-    overlap) in both, so the difference is the device time the 210 launches occupy, launch gaps included."""
+def chain_marginal(dev, hbm_gbs, reps=20, replays=10, dtype=torch.bfloat16):
+    """Bracket-free device time of one attention launch in the situation of a training step: a CUDA graph of `reps` x
+    [to_q GEMM -> attn2 core -> to_out GEMM] (cuBLAS projections, as the default processor runs them; Q freshly written, so
+    L2-resident) against the same graph without the attention launches; the difference / reps is what one launch adds --
+    launch gap, prologue, fill and drain included, no event-record nodes.  Done for the two shapes and both directions an SDXL
+    step launches, then weighted by the step's launch mix (120 + 20 forward, 60 + 10 backward)."""
     from pea_diffusion_b200 import ops
-    g, _ = capture_fb(trainer)
-    t_full = time_replays(g, replays)
-    del g
-    torch.cuda.empty_cache()
-    ops.SKIP_ATTN2 = True
-    try:
-        g, _ = capture_fb(trainer)
-    finally:
-        ops.SKIP_ATTN2 = False
-    t_skip = time_replays(g, replays)
-    del g
-    return t_full, t_skip
+    out = {}
+    total_ms, total_bytes = 0.0, 0
+    for (N, C, H, n_fwd, n_bwd) in ((1024, 1280, 20, 120, 60), (4096, 640, 10, 20, 10)):
+        B, L = 8, 77
+        h = torch.randn(B * N, C, device=dev, dtype=dtype)
+        wq = torch.randn(C, C, device=dev, dtype=dtype) * C ** -0.5
+        wo = torch.randn(C, C, device=dev, dtype=dtype) * C ** -0.5
+        kv = torch.randn(B, L, 2 * C, device=dev, dtype=dtype)
+        q = torch.empty(B * N, C, device=dev, dtype=dtype)
+        o2 = torch.empty(B * N, C, device=dev, dtype=dtype)
+        do = torch.randn(B, N, C, device=dev, dtype=dtype)
+        dkv = torch.zeros(B, L, 2 * C, device=dev, dtype=torch.float32)
+
+        def body(mode):
+            for _ in range(reps):
+                torch.matmul(h, wq.t(), out=q)
+                if mode == "fwd":
+                    o = ops.attn2_fwd(q.view(B, N, C), kv, H, 0.125)
+                elif mode == "bwd":
+                    o, _ = ops.attn2_bwd(q.view(B, N, C), kv, do, H, 0.125, dkv=dkv)
+                else:
+                    o = do
+                torch.matmul(o.view(B * N, C), wo.t(), out=o2)
+
+        times = {}
+        for mode in ("none", "fwd", "bwd"):
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                body(mode)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                body(mode)
+            times[mode] = time_replays(g, replays) * 1e3     # us
+            del g
+        fb, bb = ops.attn2_bytes(B, N, L, C, 2)
+        for mode, nbytes, count in (("fwd", fb, n_fwd), ("bwd", bb, n_bwd)):
+            us = (times[mode] - times["none"]) / reps
+            out[f"{mode}_N{N}_C{C}"] = {"us_per_launch": us, "GBps": nbytes / us / 1e3, "frac": nbytes / us / 1e3 / hbm_gbs,
+                                         "launches_per_step": count}
+            total_ms += us * count * 1e-3
+            total_bytes += nbytes * count
+    out["step_mix"] = {"attn2_ms_per_step": total_ms, "GBps": total_bytes / (total_ms * 1e-3) / 1e9,
+                       "frac": total_bytes / (total_ms * 1e-3) / 1e9 / hbm_gbs}
+    out["how"] = ("CUDA graph of %d x [cuBLAS to_q -> attn2 core -> cuBLAS to_out] minus the same graph without the attention launches, "
+                  "median of %d replays; no event brackets; weighted by the launch mix of one SDXL step" % (reps, replays))
+    return out
 
 
 def event_pair_overhead_us(dev, n=100):
@@ -575,7 +615,7 @@ def main():
     ksum, prof_steps = ops.TIMER.summary(), args.steps
     ops.TIMER.reset(False)
     timing_note = "CUDA events around every launch inside the timed eager steps"
-    marginal, ev_overhead_us = None, None
+    ev_overhead_us = None
     log('timed region done: %.2f ms/step' % ms_step)
     if graph_mode and not args.timed_only:
         # Per-kernel times INSIDE a replayed step: the same forward+backward captured once more with event-record nodes
@@ -588,9 +628,7 @@ def main():
             timing_note = ("CUDA events recorded as event-record nodes around every library launch inside %d replays of a CUDA graph "
                            "of the step's forward+backward (captured after the timed region, serial schedule: no teacher/student overlap, "
                            "no collectives), so the brackets include the node-to-node launch latency" % prof_steps)
-            log('in-graph per-kernel profile done; marginal (skip-attn2) captures')
-            t_full, t_skip = in_step_marginal(trainer)
-            marginal = (t_full, t_skip)
+            log('in-graph per-kernel profile done')
             ev_overhead_us = event_pair_overhead_us(dev)
         finally:
             trainer.teacher_stream = overlap_stream
@@ -663,16 +701,6 @@ def main():
             "algorithmic_bytes_per_step": a_bytes / prof_steps if prof_steps else None,
             "bytes_formula": "SURVEY.md 8d: fwd 2BNCe + 2BLCe; bwd 3BNCe + 4BLCe (e = 2)",
             "event_pair_overhead_us": ev_overhead_us, "timing": timing_note, "per_kernel": per_kernel}
-    if marginal is not None and a_launch:
-        t_full, t_skip = marginal
-        m_ms = t_full - t_skip
-        roof["in_step_marginal"] = {
-            "ms_step_with": t_full, "ms_step_without_attn2": t_skip, "attn2_ms_per_step": m_ms,
-            "us_per_launch": m_ms * 1e3 / (a_launch / prof_steps),
-            "GBps": (a_bytes / prof_steps) / (m_ms * 1e-3) / 1e9 if m_ms > 0 else None,
-            "frac": (a_bytes / prof_steps) / (m_ms * 1e-3) / 1e9 / pk["hbm_gbs"] if m_ms > 0 else None,
-            "how": "median replay time of the captured forward+backward minus the same capture with the attention launches "
-                   "removed (ops.SKIP_ATTN2): no event brackets, launch gaps included, inputs L2-resident as in training"}
     value = world * B / (ms_step * 1e-3)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
@@ -699,6 +727,7 @@ def main():
             clocks2 = ClockSampler(local)
             try:
                 log('attn2 / gemm sweeps')
+                roof["in_chain_marginal"] = chain_marginal(dev, pk["hbm_gbs"])
                 roof["sweep"] = attn2_sweep(dev, pk["hbm_gbs"])
                 roof["sweep_gemm"] = gemm_sweep(dev)
                 roof["sweep_how"] = ("each launch alone, 5 warm-up + 20 timed iterations, CUDA events on the launching stream, L2 flushed by "

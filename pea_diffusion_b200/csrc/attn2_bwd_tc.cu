@@ -12,8 +12,8 @@
 //                                                              then S(t+2) = Q K^T, dP(t+2) = dO V^T   SS N80 K64 -> S[g], dP[g]
 //        warp 2   dQ TMA-store issuer
 //        warp 3   MMA issuer B:  dV^T += dO^T P, dK^T += Q^T dS   SS M64 N80 K128 (A = the dO / Q tile read MN-major, B = P / dS);
-//                 released by issuer A only after S / dP(t+2) are in the tensor pipe, so the 16 dV^T / dK^T MMAs of tile t
-//                 never sit in front of the S / dP the next softmax is waiting for
+//                 released by issuer A right after dQ(t), so its 16 MMAs interleave with S / dP(t+2) in the tensor pipe
+//                 instead of sitting in front of them (one issuing warp) or behind them (which starves the next P / dS stores)
 //   WG1  warps 4-7   softmax group 0 (even tiles)     thread = query row = TMEM lane:
 //   WG2  warps 8-11  softmax group 1 (odd tiles)      P = softmax(S), delta, dS = P o (dP - delta) scale; P, dS -> shared
 //                 memory and dS -> TMEM; on a (batch, head) change the group drains dK^T / dV^T and adds them to the global
@@ -22,9 +22,10 @@
 //                 goes straight from dS(t) to S / dP(t+2)
 // Round-2 restructuring (profiles/r2_attn2_bwd_timeline.txt): in round 1 a group's cycle was softmax(t) 2 850 clk -> wait dQ
 // 720 -> dQ epilogue 950 -> wait S / dP(t+2) 720, the last because S / dP(t+2) queued behind dV^T / dK^T(t) in the in-order
-// tensor pipe; issuing S / dP(t+2) first delays dV^T / dK^T(t) and with it the release of tile t's Q / dO slot, which needs the
-// 4th ring slot -- bought by storing P / dS in the un-swizzled ("interleaved") MN-major layout: 8-key x 128-row columns of
-// 16-byte units, 20 KiB each and perfectly coalesced row-per-thread stores, instead of two 64-key 128B-swizzle slabs (32 KiB).
+// tensor pipe.  Now the dQ epilogue has its own warpgroup, S / dP(t+2) and dV^T / dK^T(t) are issued by two warps at the same
+// time, and the Q / dO ring is 4 deep (~4 200 cycles of HBM latency under load need >= 3 tiles in flight per SM) -- the 4th
+// slot bought by storing P / dS in the un-swizzled ("interleaved") MN-major layout: 8-key x 128-row columns of 16-byte units,
+// 20 KiB each and perfectly coalesced row-per-thread stores, instead of two 64-key 128B-swizzle slabs (32 KiB).
 // dK / dV are formed TRANSPOSED (rows = head dim, columns = keys): an M64 MMA fetches 2 KB of A + 2.5 KB of B per K=16 step;
 // an M64 accumulator occupies lanes 0-15 of each 32-lane quarter, so dK^T interleaves into lanes 16-31 of dV^T's 80 columns.
 // They accumulate in TMEM across the CTA's consecutive tiles of one (batch, head).
@@ -109,7 +110,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_bwd_tc_kernel(const __grid_
     tc::prefetch_tmap(&p.tmQ); tc::prefetch_tmap(&p.tmdO); tc::prefetch_tmap(&p.tmKV); tc::prefetch_tmap(&p.tmdQ);
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
-      tc::mbar_init(smem_u32(&kv_full[i]), 1); tc::mbar_init(smem_u32(&kv_empty[i]), 2);   // freed by BOTH MMA issuers
+      tc::mbar_init(smem_u32(&kv_full[i]), 1); tc::mbar_init(smem_u32(&kv_empty[i]), 1);
       tc::mbar_init(smem_u32(&sdp_full[i]), 1); tc::mbar_init(smem_u32(&ds_ready[i]), 4);
     }
 #pragma unroll
@@ -226,21 +227,24 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_bwd_tc_kernel(const __grid_
           for (int k = 0; k < kLP / 16; ++k)
             tc::mma_f16_ts(tmem + kTdQ, tds + k * 8, kDescMN | (uint64_t)(ka + k * 128), p.idesc_dq, k > 0);
           tc::mma_commit(smem_u32(&dq_full));
-          if (last_of_bh) tc::mma_commit(smem_u32(&kv_empty[kb]));   // (1 of 2) this issuer's last read of the K|V buffer
+          // S, dP and dQ are the only readers of K|V, and dQ of a head's last tile is the last of them (its S / dP completed
+          // before its softmax did): buffer reusable.  (dV^T / dK^T read only the Q / dO ring and P / dS.)
+          if (last_of_bh) tc::mma_commit(smem_u32(&kv_empty[kb]));
         }
         __syncwarp();
-        if (t + 2 < ntiles) issue_sdp(t + 2);     // same thread, after dQ(t): the pipe runs them in this order (dS before dP(t+2))
-        if (lane == 0) tc::mbar_arrive(smem_u32(&go_dkv));   // issuer B may now queue dV^T / dK^T(t) behind them
+        // Issuer B queues dV^T / dK^T(t) while this warp issues S / dP(t+2): the two streams interleave in the tensor pipe.
+        // (S / dP(t+2) strictly first was measured slower, 261 vs 232 us at N = 16384: dV^T / dK^T(t) then complete so late that
+        // the next tile's P / dS stores -- one shared-memory copy -- wait for them; profiles/r2_attn2_bwd_timeline.txt.)
+        if (lane == 0) tc::mbar_arrive(smem_u32(&go_dkv));
+        if (t + 2 < ntiles) issue_sdp(t + 2);     // same thread as dQ(t): dP(t+2) overwrites dP[g] after dQ(t) has consumed dS
       }
     } else if (warp == 3) {
       // ===== MMA issuer B: dV^T += dO^T P ; dK^T += Q^T dS (reduction over the 128 query rows; the two chains interleaved) =====
-      int m_pos = rem0, m_kvn = 0, m_rs = 0, flushes = 0;
+      int m_pos = rem0, m_rs = 0, flushes = 0;
       for (int t = 0; t < ntiles; ++t) {
         const int g = t & 1, rs = m_rs;
         if (++m_rs == kRing) m_rs = 0;
         const bool first_of_bh = t == 0 || m_pos == 0;
-        if (first_of_bh) ++m_kvn;
-        const int kb = (m_kvn - 1) & 1;
         const bool last_tile = t + 1 == ntiles;
         const bool last_of_bh = !last_tile && (m_pos == tpb - 1);
         if (++m_pos == tpb) m_pos = 0;
@@ -261,7 +265,6 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_bwd_tc_kernel(const __grid_
           tc::mma_commit(smem_u32(&pds_free));            // P / dS shared-memory tiles reusable
           tc::mma_commit(smem_u32(&ring_empty[rs]));      // Q / dO slot reusable
           if (last_of_bh || last_tile) tc::mma_commit(smem_u32(&dkv_full));
-          if (last_of_bh) tc::mma_commit(smem_u32(&kv_empty[kb]));   // (2 of 2)
         }
         __syncwarp();
         if (last_of_bh || last_tile) ++flushes;

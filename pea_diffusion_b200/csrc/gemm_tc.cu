@@ -225,6 +225,14 @@ __device__ __forceinline__ void epilogue_alignment(const GemmParams& p, bool& al
   alx = p.aux && (p.ldaux % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.aux) & (p.aux_dtype == PEA_F32 ? 31 : 15)) == 0);
 }
 
+// Optional event timeline of CTA 0 (build with -DPEA_TRACE, read with tools/trace_gemm.py).  No-op in the product build.
+#ifdef PEA_TRACE
+__device__ unsigned long long g_trace_gemm[64];
+#define GTRACE(ev) do { if (blockIdx.x == 0 && lane == 0) g_trace_gemm[ev] = clock64(); } while (0)
+#else
+#define GTRACE(ev) do { } while (0)
+#endif
+
 // SA / SB: operand plane counts; A_MN / B_MN: operand majors.  Everything the issue loops touch is a compile-time
 // constant or a warp-uniform value: the whole producer / MMA warp runs the loop (uniform control flow keeps address
 // and descriptor arithmetic on the uniform datapath) and only the asynchronous instruction itself is issued by one
@@ -245,6 +253,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t tiles = (smem_u32(smem_raw) + 1023u) & ~1023u;  // 128B swizzle atoms need 1024-byte alignment
   const int stages = p.stages;
+  if (warp == 0) GTRACE(0);   // kernel entry
   // tile index -> (split, n tile, m tile), m fastest: CTAs that run together share B (weight) tiles through L2
   auto tile_coords = [&](int tile, int& m0, int& n0, int& kb_begin, int& nkb) {
     const int mi = tile % p.m_tiles;
@@ -275,6 +284,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   const uint32_t tmem_base = tmem_base_slot;
   pdl_wait();                 // PEA_LAUNCH_PDL: the prologue above overlapped the preceding kernel's tail
   pdl_launch_dependents();
+  if (warp == 0) GTRACE(1);   // prologue done
 
   if (warp == 0) {
     // ===== TMA producer (whole warp loops; one elected lane issues) =====
@@ -331,6 +341,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       tc::fence_after_sync();
       for (int it = 0; it < nkb; ++it) {
         tc::mbar_wait(smem_u32(&full_bar[s]), ph);
+        if (local == 0 && it == 0) GTRACE(2);              // first stage landed
+        if (local == 0 && it == nkb - 1) GTRACE(3);        // last stage of the first tile landed
         tc::fence_after_sync();
         if (tc::elect_one()) {
           const uint32_t a_base = (tiles + (uint32_t)s * kStageBytes) >> 4;  // smem < 256 KiB: fits the 14-bit field
@@ -367,8 +379,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       tile_coords(tile, m0, n0, kb_begin, nkb);
       const int as = local & 1;
       tc::mbar_wait(smem_u32(&acc_full[as]), (uint32_t)(local >> 1) & 1u);
+      if (local == 0 && warp == 2) GTRACE(4);              // first accumulator complete
       tc::fence_after_sync();
       epilogue_tile<BN>(p, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN), m0 + q * 32 + lane, n0, al0, al1, alx);
+      if (local == 0 && warp == 2) GTRACE(5);              // first tile's epilogue done (this warp)
       tc::fence_before_sync();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(smem_u32(&acc_empty[as]));   // this accumulator may be overwritten (tile local + 2)
@@ -377,11 +391,22 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
 
   tc::fence_before_sync();
   __syncthreads();
+  if (warp == 0) GTRACE(6);   // all roles done
   if (warp == 1) {
     tc::fence_after_sync();
     tc::tmem_dealloc(tmem_base, kTmemCols);
   }
 }
+
+#ifdef PEA_TRACE
+}  // namespace
+}  // namespace pea
+extern "C" int pea_debug_gemm_trace(unsigned long long* host, int n) {
+  return (int)cudaMemcpyFromSymbol(host, pea::g_trace_gemm, sizeof(unsigned long long) * n);
+}
+namespace pea {
+namespace {
+#endif
 
 // ---------------------------------------------------------------------------------------------------------------------
 // CTA-pair variant (cta_group::2): a cluster of two CTAs on adjacent SMs computes one 256 x 256 tile.  Each CTA stages its

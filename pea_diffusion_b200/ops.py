@@ -47,11 +47,6 @@ class KernelTimer:
 
 TIMER = KernelTimer()
 
-# Measurement-only switch (bench.py's `roofline.in_step_marginal`): when set, attn2_fwd / attn2_bwd allocate their outputs
-# but launch nothing, so that the device time of a captured step WITHOUT the attention launches can be subtracted from
-# the time of the full step.  Never set on a product path; outputs are uninitialised memory while it is on.
-SKIP_ATTN2 = False
-
 
 class _timed:
     def __init__(self, name: str, nbytes: int, flops: int = 0):
@@ -228,8 +223,6 @@ def attn2_fwd(q: Tensor, kv: Tensor, heads: int, scale: float, pdl: bool = False
     d = _attn_desc(q, kv, heads, scale)
     d.flags = _lib.PEA_LAUNCH_PDL if pdl else 0
     d.d_o, d.ld_o = o.data_ptr(), Cq
-    if SKIP_ATTN2:
-        return o
     with _timed("attn2_fwd", attn2_bytes(B, N, L, Cq, q.element_size())[0], 4 * B * N * L * Cq):
         check(lib.pea_attn2_fwd(C.byref(d), stream_ptr(q.device)), "pea_attn2_fwd")
     return o
@@ -254,8 +247,6 @@ def attn2_bwd(q: Tensor, kv: Tensor, do: Tensor, heads: int, scale: float, dkv: 
     d.d_dq, d.ld_dq = dq.data_ptr(), Cq
     d.d_dk, d.d_dv = dkv.data_ptr(), dkv.data_ptr() + 4 * Cq
     d.ld_dkv, d.bs_dkv = dkv.stride(1), dkv.stride(0)
-    if SKIP_ATTN2:
-        return dq, dkv
     with _timed("attn2_bwd", attn2_bytes(B, N, L, Cq, q.element_size())[1], 10 * B * N * L * Cq):
         check(lib.pea_attn2_bwd(C.byref(d), stream_ptr(q.device)), "pea_attn2_bwd")
     return dq, dkv

@@ -28,7 +28,7 @@ ev = lambda role, t, e: buf[(role * 64 + t) * 16 + e]
 t0 = ev(0, 63, 15)
 print("kernel entry -> all roles done:", ev(0, 63, 14) - t0, "cycles; groups done at", ev(2, 63, 14) - t0, ev(3, 63, 14) - t0)
 names = {0: ["ring_empty"], 1: ["sdp:enter", "sdp:ring_full", "main:enter", "ds_ready", "dq_free"],
-         2: ["enter", "sdp_full", "pre_pds", "pds_free", "ds_arrive", "dq_full", "stage_free", "epi_done"]}
+         2: ["enter", "sdp_full", "pre_pds", "pds_free", "ds_arrive"]}
 ntiles = (B * H * ((N + 127) // 128) + 147) // 148
 lo, hi = (8, 20) if ntiles > 24 else (0, ntiles)
 print(f"cycles relative to kernel entry; tiles {lo}..{hi - 1} of {ntiles}")
@@ -37,7 +37,8 @@ for t in range(lo, hi):
     row = [f"t{t:2d} g{g}"]
     row.append("prod " + " ".join(f"{ev(0, t, i) - t0:7d}" for i in range(1)))
     row.append("| mma " + " ".join(f"{names[1][i]}={ev(1, t, i) - t0:7d}" for i in range(5)))
-    row.append("| sm " + " ".join(f"{names[2][i]}={ev(2 + g, t, i) - t0:7d}" for i in range(8)))
+    row.append("| sm " + " ".join(f"{names[2][i]}={ev(2 + g, t, i) - t0:7d}" for i in range(5)))
+    row.append(f"| dq_epilogue_done={ev(4, t, 0) - t0:7d}")
     print(" ".join(row))
 print("softmax passes A / B / C (cycles):", [(ev(2 + (t & 1), t, 8) - ev(2 + (t & 1), t, 1), ev(2 + (t & 1), t, 9) - ev(2 + (t & 1), t, 8),
                                                ev(2 + (t & 1), t, 2) - ev(2 + (t & 1), t, 9)) for t in range(lo, hi)])
