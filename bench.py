@@ -61,7 +61,7 @@ def parse():
     ap.add_argument("--comm-dtype", default="fp32", choices=["fp32", "bf16"], help="payload of the adapter-gradient all-reduce")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager step instead of the CUDA-graph replay")
-    ap.add_argument("--no-capture-comm", action="store_true", help="keep the NCCL all-reduce outside the CUDA graph")
+    ap.add_argument("--capture-comm", action="store_true", help="capture the NCCL all-reduce into the step's CUDA graph (experimental)")
     ap.add_argument("--overlap-teacher", type=int, default=1, help="1: teacher forward on its own stream, concurrent with the student forward (0: in line)")
     ap.add_argument("--timed-only", action="store_true", help="only the timed region (ncu launch-list runs)")
     ap.add_argument("--no-sweep", action="store_true")
@@ -570,7 +570,7 @@ def main():
 
     def make_trainer(overlap):
         return KDTrainer(student, teacher, adapter, "sdxl", lr=1e-5, cuda_graph=graph_mode, overlap_teacher=overlap,
-                         comm_dtype=torch.bfloat16 if args.comm_dtype == "bf16" else None, capture_comm=not args.no_capture_comm,
+                         comm_dtype=torch.bfloat16 if args.comm_dtype == "bf16" else None, capture_comm=args.capture_comm,
                          loss_scale=65536.0 if args.dtype == "fp16" else None, dynamic_loss_scale=args.dtype == "fp16")
 
     trainer = make_trainer(bool(args.overlap_teacher))
@@ -707,7 +707,8 @@ def main():
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype,
         "data": "synthetic", "config": workload_config(args, world),
         "execution": {"adapter_precision": ad_prec, "comm_dtype": args.comm_dtype,
-                      "step": ("ONE CUDA graph per step: forward + backward" + (" + bucketed NCCL all-reduce (captured)" if world > 1 and not args.no_capture_comm else "") +
+                      "step": ("ONE CUDA graph per step: forward + backward" + (" + bucketed NCCL all-reduce (captured)" if world > 1 and args.capture_comm else "") +
+                               (", then two NCCL bucket all-reduces of the flat gradient buffer" if world > 1 and not args.capture_comm else "") +
                                ", then the fused AdamW launch" if graph_mode else "eager") +
                               ("; teacher forward on a parallel graph branch" if args.overlap_teacher else "")},
         "e2e": {"value": world * B / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 16,

@@ -238,11 +238,12 @@ class GradAllReducer:
             self._pending.append(dist.all_reduce(buf, op=self._op, group=self.group, async_op=True))
 
     def finish(self) -> None:
-        for w in self._pending:
-            w.wait()
-        self._pending.clear()
-        if self._comm_stream is not None:
-            torch.cuda.current_stream().wait_stream(self._comm_stream)
+        if self._pending:
+            for w in self._pending:
+                w.wait()
+            self._pending.clear()
+            if self._comm_stream is not None:     # only when something was launched there: inside a CUDA-graph capture that
+                torch.cuda.current_stream().wait_stream(self._comm_stream)   # carries no collectives the side stream is not captured
         if self.comm is not self.flat:
             self.flat.copy_(self.comm)          # widen the reduced 16-bit payload into the fp32 gradients
         if self._post_scale != 1.0:
@@ -291,9 +292,12 @@ class KDTrainer:
     train_sdxl_zh.sh:22-31).
 
     ``cuda_graph=True`` captures forward + backward of the step (adapter, both UNets, loss: every kernel of this library
-    and of the PyTorch shell) AND the gradient all-reduce (a forked branch that starts as soon as the head's dW is
-    written) into ONE CUDA graph on the first call and replays it afterwards; batches are copied into the graph's static
-    input buffers.  Only the fused AdamW step stays outside.  Shapes must then stay fixed.
+    and of the PyTorch shell) into ONE CUDA graph on the first call and replays it afterwards; batches are copied into the
+    graph's static input buffers.  After the replay two NCCL launches reduce the flat gradient buffer (bucket by bucket, on
+    the side stream) and the fused AdamW step follows; shapes must stay fixed.  (``capture_comm=True`` puts the collectives
+    into the graph as a forked branch; with torch 2.11 / NCCL 2.28 the capture fails with cudaErrorStreamCaptureIsolation on a
+    2-GPU box, so it is off by default -- in eager mode the head's bucket IS in flight while the rest of the adapter's backward
+    runs.)
 
     ``loss_scale`` (fp16 training, the reference's ``--precision 16``, train_sdxl_zh.sh:89): the loss is scaled before
     backward -- the fused KD pass applies the scale before rounding its gradients to fp16 --, gradients are unscaled and
@@ -304,7 +308,7 @@ class KDTrainer:
     def __init__(self, student: nn.Module, teacher: nn.Module, adapter: nn.Module, variant: str = "sdxl", lr: float = 1e-5,
                  betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0, feature_weight: float = 0.1,
                  process_group=None, cuda_graph: bool = False, overlap_teacher: bool = False,
-                 comm_dtype: Optional[torch.dtype] = None, capture_comm: bool = True,
+                 comm_dtype: Optional[torch.dtype] = None, capture_comm: bool = False,
                  loss_scale: Optional[float] = None, dynamic_loss_scale: bool = False, growth_interval: int = 2000):
         self.student, self.teacher, self.adapter, self.variant = student, teacher, adapter, variant
         self.feature_weight = feature_weight
@@ -366,7 +370,7 @@ class KDTrainer:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self._graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self._graph, stream=side, capture_error_mode="thread_local" if world > 1 else "global"):
+        with torch.cuda.graph(self._graph, stream=side, capture_error_mode="thread_local" if (world > 1 and self.capture_comm) else "global"):
             self._static_out = self._forward_backward(self._static_in)
         self.reducer.world = world
 
