@@ -67,6 +67,8 @@ def parse():
     ap.add_argument("--no-sweep", action="store_true")
     ap.add_argument("--no-infer", action="store_true")
     ap.add_argument("--tiny", action="store_true", help="tiny shell (debug only; the JSON line says so)")
+    ap.add_argument("--workload", default="train", choices=["train", "infer"],
+                    help="infer: BASELINE.json configs[4] alone (30 forward-only UNet calls, fp16, UNet batch 8) as its own JSON line")
     return ap.parse_args()
 
 
@@ -541,6 +543,16 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback); use --impl reference for the host arm"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    if args.workload == "infer":
+        if rank == 0:
+            clocks = ClockSampler(local)
+            res = infer_subrun(dev, steps=30)
+            emit({"metric": "SDXL-1024 inference UNet calls/s (30-step denoise loop, UNet batch 8)", "unit": "calls/s",
+                  "value": 1e3 / res["fused"]["ms_per_unet_call"], "n_gpus": 1, "steps": 30, "warmup": 30, "ms_per_step": res["fused"]["ms_per_unet_call"],
+                  "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp16", "data": "synthetic",
+                  "config": {"workload": res["workload"]}, "infer": res, "clocks": clocks.stop(),
+                  "gpu_launches": res["fused"]["library_launches"]})
+        return
     if world > 1:
         # stdout carries exactly ONE JSON line: NCCL's banner / debug output (stdout by default) goes to stderr
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")

@@ -421,7 +421,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_bwd_tc_kernel(const __grid_
         }
         tc::fence_before_sync();
         __syncwarp();
-        if (lane == 0) tc::mbar_arrive(smem_u32(&dkv_free));    // TMEM dK / dV may be overwritten by the next head
+        if (lane == 0 && !last_tile) tc::mbar_arrive(smem_u32(&dkv_free));   // TMEM dK / dV may be overwritten by the next head
         {
           // quarter q holds rows 16q .. 16q+15 of dV^T in lanes 0-15 and of dK^T in lanes 16-31
           float* ptr = (lane < 16 ? p.dv : p.dk) + (long long)b * p.bs_dkv + h * kD + q * 16 + (lane & 15);

@@ -44,6 +44,8 @@ struct GemmParams {
   int kb_total, kb_per_split;
   int m_tiles, n_tiles, splits, total_tiles;
   int stages;
+  int bn;                    // output tile width (multiple of 16, 32..256), chosen per problem against the wave count
+  uint32_t b_tile_bytes;     // one B plane of one stage: bn x 128 B (K-major) or ceil(bn / 64) x 8 KiB (MN-major slabs)
   uint32_t idesc;
   float alpha;
   const float* bias;
@@ -53,6 +55,7 @@ struct GemmParams {
   void* out0; int out0_dtype; long long ldo0; int out0_mode;  // 0 store, 1 +=, 2 atomic add
   void* out1[3]; int out1_nsplit; int out1_dtype; long long ldo1;
   int pdl;
+  int epi_plain;   // out0 = alpha * acc (+ bias), plain vectorised store: the specialised epilogue below
 };
 
 // ---- epilogue helpers: 8 consecutive columns of one row -----------------------------------------------------------
@@ -160,10 +163,73 @@ __device__ __forceinline__ float round16(float v, int dtype) {
   return dtype == PEA_F16 ? __half2float(__float2half_rn(v)) : __bfloat162float(__float2bfloat16_rn(v));
 }
 
+// Specialised epilogue for the common case out0 = alpha * acc (+ bias[n]) stored once (any dtype, N % 8 == 0, aligned): 32
+// accumulator columns per TMEM load, the next load in flight while the current columns are converted and stored with 128-bit
+// stores.  The general body below walks ~100 mostly-branch instructions per 8 columns in a single warp per scheduler:
+// 7 600 cycles for a 128 x 128 tile (profiles/r2_gemm_timeline.txt) -- as long as the whole K = 1024 main loop of the
+// one-wave adapter GEMMs.  This one takes ~1 500.
+// 32 accumulator columns of one row: alpha, bias, convert, four 128-bit (two for 16-bit outputs: 8 columns = 16 B) stores.
+template <int DT>
+__device__ __forceinline__ void plain_store32(const GemmParams& p, const uint32_t (&v)[32], int row, int nb, int n_end, float alpha) {
+#pragma unroll
+  for (int g8 = 0; g8 < 4; ++g8) {
+    const int n = nb + g8 * 8;
+    if (n < n_end) {        // N and bn are multiples of 8: a group of 8 columns is either all in or all out
+      float f[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = alpha * __uint_as_float(v[g8 * 8 + j]);
+      if (p.bias) {
+        const float4 b0 = *reinterpret_cast<const float4*>(p.bias + n), b1 = *reinterpret_cast<const float4*>(p.bias + n + 4);
+        f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w; f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+      }
+      const long long off = (long long)row * p.ldo0 + n;
+      if constexpr (DT == PEA_F32) {
+        float* o = static_cast<float*>(p.out0) + off;
+        *reinterpret_cast<float4*>(o) = make_float4(f[0], f[1], f[2], f[3]);
+        *reinterpret_cast<float4*>(o + 4) = make_float4(f[4], f[5], f[6], f[7]);
+      } else if constexpr (DT == PEA_BF16) {
+        *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out0) + off) =
+            make_uint4(pack2<__nv_bfloat16>(f[0], f[1]), pack2<__nv_bfloat16>(f[2], f[3]), pack2<__nv_bfloat16>(f[4], f[5]), pack2<__nv_bfloat16>(f[6], f[7]));
+      } else {
+        *reinterpret_cast<uint4*>(static_cast<__half*>(p.out0) + off) =
+            make_uint4(pack2<__half>(f[0], f[1]), pack2<__half>(f[2], f[3]), pack2<__half>(f[4], f[5]), pack2<__half>(f[6], f[7]));
+      }
+    }
+  }
+}
+
+template <int DT>
+__device__ __forceinline__ void epilogue_tile_plain_dt(const GemmParams& p, uint32_t tacc, int row, int n0, int bn) {
+  const bool row_ok = row < p.M;
+  const float alpha = p.alpha;
+  const int n_end = min(p.N, n0 + bn);     // columns past the tile belong to the next tile (or to nobody)
+  uint32_t va[32], vb[32];
+  tc::tmem_ld32(tacc, va);
+  // two 32-column chunks per (rolled) iteration, ping-pong buffers: the next chunk's TMEM load is always in flight.  Rolled so
+  // that the executed code stays a few KB (a fully unrolled 256-column body is 40 KB: it thrashes the instruction cache).
+#pragma unroll 1
+  for (int c = 0; c * 32 < bn; c += 2) {
+    tc::tmem_ld_wait();
+    if ((c + 1) * 32 < bn) tc::tmem_ld32(tacc + (uint32_t)((c + 1) * 32), vb);     // warp-uniform
+    if (row_ok) plain_store32<DT>(p, va, row, n0 + c * 32, n_end, alpha);
+    if ((c + 1) * 32 < bn) {
+      tc::tmem_ld_wait();
+      if ((c + 2) * 32 < bn) tc::tmem_ld32(tacc + (uint32_t)((c + 2) * 32), va);
+      if (row_ok) plain_store32<DT>(p, vb, row, n0 + (c + 1) * 32, n_end, alpha);
+    }
+  }
+}
+
+__device__ __forceinline__ void epilogue_tile_plain(const GemmParams& p, uint32_t tacc, int row, int n0, int bn) {
+  if (p.out0_dtype == PEA_F32) epilogue_tile_plain_dt<PEA_F32>(p, tacc, row, n0, bn);
+  else if (p.out0_dtype == PEA_BF16) epilogue_tile_plain_dt<PEA_BF16>(p, tacc, row, n0, bn);
+  else epilogue_tile_plain_dt<PEA_F16>(p, tacc, row, n0, bn);
+}
+
 // Epilogue of one 128-row x BN-column accumulator tile for one thread (= one output row): TMEM -> registers -> fused math
 // -> global.  `tacc` = TMEM address of the accumulator's column 0 in this warp's lane quadrant.
-template <int BN>
-__device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tacc, int row, int n0, bool al0, bool al1, bool alx) {
+__device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tacc, int row, int n0, int bn, bool al0, bool al1, bool alx) {
+  if (p.epi_plain) { epilogue_tile_plain(p, tacc, row, n0, bn); return; }
   const bool row_ok = row < p.M;
   const float* radd = (p.rowadd && row_ok) ? p.rowadd + (long long)(row / p.rowadd_group) * p.N : nullptr;
   // ONE rolled copy of the 8-column body.  With every dtype / mode variant inlined it is ~1.5 k instructions; unrolled four
@@ -172,13 +238,14 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tacc
   // the next 8 columns is issued before the current ones are processed, so its latency stays hidden.
   uint32_t v[8];
   tmem_ld8(tacc, v);
+  const int ngroups = bn >> 3;
 #pragma unroll 1
-  for (int c = 0; c < BN / 8; ++c) {
+  for (int c = 0; c < ngroups; ++c) {
     tc::tmem_ld_wait();
     float f[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) f[j] = p.alpha * __uint_as_float(v[j]);
-    if (c + 1 < BN / 8) tmem_ld8(tacc + (uint32_t)((c + 1) * 8), v);   // warp-uniform: all 32 lanes issue it
+    if (c + 1 < ngroups) tmem_ld8(tacc + (uint32_t)((c + 1) * 8), v);   // warp-uniform: all 32 lanes issue it
     const int n = n0 + c * 8;
     if (row_ok && n < p.N) {
       const int valid = min(8, p.N - n);
@@ -238,7 +305,7 @@ __device__ unsigned long long g_trace_gemm[64];
 // and descriptor arithmetic on the uniform datapath) and only the asynchronous instruction itself is issued by one
 // elected lane.  A single-lane loop with runtime plane / major branches measured ~430 cycles between MMAs (the
 // 128x128x16 MMA itself takes 64): r1 ncu capture profiles/gemm_r1_before.txt.
-template <int SA, int SB, int A_MN, int B_MN, int BN>
+template <int SA, int SB, int A_MN, int B_MN>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
@@ -247,9 +314,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   __shared__ uint32_t tmem_base_slot;
 
   constexpr int S = SA > SB ? SA : SB;
-  constexpr uint32_t kBTile = (uint32_t)BN * BK * 2;                       // B plane bytes per stage
-  constexpr uint32_t kStageBytes = (uint32_t)SA * kTileBytes + (uint32_t)SB * kBTile;
-  constexpr uint32_t kTmemCols = 2 * BN;
+  const int bn = p.bn;
+  const uint32_t kBTile = p.b_tile_bytes;                                  // B plane bytes per stage
+  const uint32_t kStageBytes = (uint32_t)SA * kTileBytes + (uint32_t)SB * kBTile;
+  constexpr uint32_t kTmemCols = 512;                                      // two accumulators of up to 256 columns
+  constexpr uint32_t kAccStride = 256;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t tiles = (smem_u32(smem_raw) + 1023u) & ~1023u;  // 128B swizzle atoms need 1024-byte alignment
   const int stages = p.stages;
@@ -259,7 +328,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     const int mi = tile % p.m_tiles;
     const int rest = tile / p.m_tiles;
     const int ni = rest % p.n_tiles, z = rest / p.n_tiles;
-    m0 = mi * BM; n0 = ni * BN;
+    m0 = mi * BM; n0 = ni * bn;
     kb_begin = z * p.kb_per_split;
     nkb = min(p.kb_total, kb_begin + p.kb_per_split) - kb_begin;
   };
@@ -312,7 +381,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             if (!B_MN) tc::tma_load_2d(d, &p.tmB[j], fb, k0, n0);
             else {
 #pragma unroll
-              for (int c = 0; c < BN / 64; ++c) tc::tma_load_2d(d + c * 8192, &p.tmB[j], fb, n0 + c * 64, k0);
+              for (int c = 0; c < 4; ++c)
+                if (c * 64 < bn) tc::tma_load_2d(d + c * 8192, &p.tmB[j], fb, n0 + c * 64, k0);
             }
           }
         }
@@ -336,7 +406,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       int m0, n0, kb_begin, nkb;
       tile_coords(tile, m0, n0, kb_begin, nkb);
       const int as = local & 1;
-      const uint32_t tmem_acc = tmem_base + (uint32_t)as * BN;
+      const uint32_t tmem_acc = tmem_base + (uint32_t)as * kAccStride;
       tc::mbar_wait(smem_u32(&acc_empty[as]), ((uint32_t)(local >> 1) & 1u) ^ 1u);   // epilogue drained this accumulator
       tc::fence_after_sync();
       for (int it = 0; it < nkb; ++it) {
@@ -381,7 +451,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       tc::mbar_wait(smem_u32(&acc_full[as]), (uint32_t)(local >> 1) & 1u);
       if (local == 0 && warp == 2) GTRACE(4);              // first accumulator complete
       tc::fence_after_sync();
-      epilogue_tile<BN>(p, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN), m0 + q * 32 + lane, n0, al0, al1, alx);
+      epilogue_tile(p, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)as * kAccStride, m0 + q * 32 + lane, n0, bn, al0, al1, alx);
       if (local == 0 && warp == 2) GTRACE(5);              // first tile's epilogue done (this warp)
       tc::fence_before_sync();
       __syncwarp();
@@ -534,7 +604,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc2_kernel(const __grid_cons
       const int as = local & 1;
       tc::mbar_wait(smem_u32(&acc_full[as]), (uint32_t)(local >> 1) & 1u);
       tc::fence_after_sync();
-      epilogue_tile<BN>(p, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN), m0 + (int)rank * 128 + q * 32 + lane, n0, al0, al1, alx);
+      epilogue_tile(p, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN), m0 + (int)rank * 128 + q * 32 + lane, n0, BN, al0, al1, alx);
       tc::fence_before_sync();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive_cluster(as ? leader_empty1 : leader_empty0);
@@ -550,22 +620,22 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc2_kernel(const __grid_cons
   }
 }
 
-template <int SA, int SB, int A_MN, int B_MN, int BN>
+template <int SA, int SB, int A_MN, int B_MN>
 int launch(const GemmParams& p, int ctas, size_t smem, cudaStream_t st) {
   static std::atomic<unsigned long long> attr_done{0};
-  if (int rc = ensure_dynamic_smem(gemm_tc_kernel<SA, SB, A_MN, B_MN, BN>, (int)(kSmemBudget + 1024), attr_done)) return rc;
-  PEA_CUDA(launch_ex(gemm_tc_kernel<SA, SB, A_MN, B_MN, BN>, ctas, kThreads, smem, st, p.pdl != 0, p));
+  if (int rc = ensure_dynamic_smem(gemm_tc_kernel<SA, SB, A_MN, B_MN>, (int)(kSmemBudget + 1024), attr_done)) return rc;
+  PEA_CUDA(launch_ex(gemm_tc_kernel<SA, SB, A_MN, B_MN>, ctas, kThreads, smem, st, p.pdl != 0, p));
   PEA_LAUNCH_CHECK();
   return PEA_OK;
 }
 
-template <int SA, int SB, int BN>
+template <int SA, int SB>
 int dispatch_major(const GemmParams& p, int ctas, size_t smem, cudaStream_t st) {
   switch (p.a_mn * 2 + p.b_mn) {
-    case 0: return launch<SA, SB, 0, 0, BN>(p, ctas, smem, st);
-    case 1: return launch<SA, SB, 0, 1, BN>(p, ctas, smem, st);
-    case 2: return launch<SA, SB, 1, 0, BN>(p, ctas, smem, st);
-    default: return launch<SA, SB, 1, 1, BN>(p, ctas, smem, st);
+    case 0: return launch<SA, SB, 0, 0>(p, ctas, smem, st);
+    case 1: return launch<SA, SB, 0, 1>(p, ctas, smem, st);
+    case 2: return launch<SA, SB, 1, 0>(p, ctas, smem, st);
+    default: return launch<SA, SB, 1, 1>(p, ctas, smem, st);
   }
 }
 
@@ -599,17 +669,13 @@ int dispatch_pair(const GemmParams& p, int pairs, size_t smem, cudaStream_t st) 
   }
 }
 
-// BN = 256 tiles exist for single-plane operands only (the throughput mode); the fp32-accurate plane modes use 128.
-bool has_bn256(int sa, int sb) { return sa == 1 && sb == 1; }
-
-int dispatch(const GemmParams& p, int bn, int ctas, size_t smem, cudaStream_t st) {
-  if (bn == 256) return dispatch_major<1, 1, 256>(p, ctas, smem, st);
+int dispatch(const GemmParams& p, int ctas, size_t smem, cudaStream_t st) {
   switch (p.sa * 4 + p.sb) {
-    case 1 * 4 + 1: return dispatch_major<1, 1, 128>(p, ctas, smem, st);
-    case 2 * 4 + 1: return dispatch_major<2, 1, 128>(p, ctas, smem, st);
-    case 1 * 4 + 2: return dispatch_major<1, 2, 128>(p, ctas, smem, st);
-    case 2 * 4 + 2: return dispatch_major<2, 2, 128>(p, ctas, smem, st);
-    case 3 * 4 + 3: return dispatch_major<3, 3, 128>(p, ctas, smem, st);
+    case 1 * 4 + 1: return dispatch_major<1, 1>(p, ctas, smem, st);
+    case 2 * 4 + 1: return dispatch_major<2, 1>(p, ctas, smem, st);
+    case 1 * 4 + 2: return dispatch_major<1, 2>(p, ctas, smem, st);
+    case 2 * 4 + 2: return dispatch_major<2, 2>(p, ctas, smem, st);
+    case 3 * 4 + 3: return dispatch_major<3, 3>(p, ctas, smem, st);
   }
   set_error("gemm: plane combination (%d, %d) is not instantiated (supported: 1x1, 2x1, 1x2, 2x2, 3x3)", p.sa, p.sb);
   return PEA_EUNSUPPORTED;
@@ -709,16 +775,37 @@ extern "C" int pea_gemm(const pea_gemm_desc* g, void* stream) {
   p.sa = g->nsplit_a; p.sb = g->nsplit_b;
   p.a_mn = g->a_kmajor ? 0 : 1; p.b_mn = g->b_kmajor ? 0 : 1;
   const bool fp16 = g->in_dtype == PEA_F16;
-  // 128 x 256 tiles when that still leaves at least one tile per SM (halves A re-reads, 2/3 instead of 1/2 tensor duty
-  // under the shared-memory bandwidth bound); otherwise 128 x 128 for parallelism.
+  // Tile width: the multiple of 16 in [32, 256] that minimises  waves x (K blocks x time per stage + epilogue)  with
+  //   time per stage = max(MMA: 2 bn clk per plane product, feed: stage bytes / ~60 B per clk of L2 -> shared memory per SM).
+  // Wide tiles halve the A re-reads and raise the tensor duty under the shared-memory bandwidth bound, but a one-wave
+  // problem wants as many CTAs as fit in ONE wave: M = 1232, N = 2048 ran 160 tiles of 128 x 128 on 148 SMs -- twelve CTAs did
+  // two -- and now runs 130 tiles of 128 x 160 (profiles/r2_gemm_timeline.txt).  PEA_GEMM_BN forces a width (A/B runs).
   const int m_tiles = (g->M + BM - 1) / BM;
+  const int kb_all = (g->K + BK - 1) / BK;
+  const int nsplit_k = g->split_k > 1 ? (g->split_k < kb_all ? g->split_k : kb_all) : 1;
+  const int nprod = [&] { int n = 0; const int S = p.sa > p.sb ? p.sa : p.sb; for (int i = 0; i < p.sa; ++i) for (int j = 0; j < p.sb; ++j) n += (i + j < S); return n; }();
   int bn = 128;
-  if (has_bn256(p.sa, p.sb) && g->split_k <= 1 && (long long)m_tiles * ((g->N + 255) / 256) >= num_sms()) bn = 256;
+  {
+    static int forced = -2;
+    if (forced == -2) { const char* e = getenv("PEA_GEMM_BN"); forced = e ? atoi(e) : -1; }
+    double best = 1e30;
+    const int sms = num_sms();
+    for (int cand = 256; cand >= 32; cand -= 16) {
+      const size_t stage = (size_t)p.sa * kTileBytes + (size_t)p.sb * (p.b_mn ? (size_t)((cand + 63) / 64) * 8192 : (size_t)cand * 128);
+      if (kSmemBudget / stage < 2) continue;                       // needs at least a double buffer
+      const long long tiles = (long long)m_tiles * ((g->N + cand - 1) / cand) * nsplit_k;
+      const double waves = (double)((tiles + sms - 1) / sms);
+      const double t_stage = fmax(2.0 * cand * nprod, (double)stage / 60.0);
+      const double cost = waves * ((double)((kb_all + nsplit_k - 1) / nsplit_k) * t_stage + 12.0 * cand);
+      if (cost < best * 0.999) { best = cost; bn = cand; }
+    }
+    if (forced >= 32 && forced <= 256 && forced % 16 == 0) bn = forced;
+  }
   // CTA pairs (256 x 256 per two SMs) when there is a pair tile per SM pair and the row padding to 256 does not eat the
   // gain (measured: 1 329 vs 1 169 TF/s at 4096^3, x1.14; at M = 616 the 768-row padding loses: 895 vs 1 031 TF/s);
   // PEA_GEMM_PAIR=0/1 forces the choice for A/B runs.
   bool pair = false;
-  if (bn == 256) {
+  if (bn == 256 && p.sa == 1 && p.sb == 1 && g->split_k <= 1) {   // the pair kernel is single-plane, no split-K
     const long long pm = (g->M + 255) / 256, pn = (g->N + 255) / 256;
     const double eff_pair = (double)g->M / (256.0 * pm), eff_single = (double)g->M / (128.0 * m_tiles);
     pair = pm * pn >= num_sms() / 2 && eff_pair * 1.12 > eff_single;
@@ -742,7 +829,7 @@ extern "C" int pea_gemm(const pea_gemm_desc* g, void* stream) {
     int rc = encode_tmap_16bit(&p.tmB[j], g->d_B[j], 2, dims, str, box, fp16);
     if (rc != PEA_OK) return rc;
   }
-  p.kb_total = (g->K + BK - 1) / BK;
+  p.kb_total = kb_all;
   int splits = g->split_k > 1 ? g->split_k : 1;
   if (splits > 1) {
     PEA_CHECK_ARG(g->d_out0 && g->out0_dtype == PEA_F32 && g->out0_accumulate && g->out1_nsplit == 0 && !g->d_bias && !g->d_aux && !g->d_rowadd,
@@ -755,7 +842,9 @@ extern "C" int pea_gemm(const pea_gemm_desc* g, void* stream) {
   p.n_tiles = (g->N + bn - 1) / bn;
   p.splits = splits;
   p.total_tiles = p.m_tiles * p.n_tiles * splits;
-  const size_t stage_bytes = (size_t)p.sa * kTileBytes + (size_t)p.sb * bn * BK * 2;
+  p.bn = bn;
+  p.b_tile_bytes = p.b_mn ? (uint32_t)((bn + 63) / 64) * 8192u : (uint32_t)bn * 128u;
+  const size_t stage_bytes = (size_t)p.sa * kTileBytes + (size_t)p.sb * p.b_tile_bytes;
   int stages = (int)(kSmemBudget / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   p.stages = stages;
@@ -778,6 +867,13 @@ extern "C" int pea_gemm(const pea_gemm_desc* g, void* stream) {
   }
   p.out1_nsplit = g->out1_nsplit; p.out1_dtype = g->out1_dtype; p.ldo1 = g->ldo1;
   p.pdl = (g->flags & PEA_LAUNCH_PDL) ? 1 : 0;
+  {
+    static int disable = -1;   // PEA_GEMM_PLAIN_EPI=0: general epilogue everywhere (A/B runs)
+    if (disable < 0) { const char* e = getenv("PEA_GEMM_PLAIN_EPI"); disable = (e && e[0] == '0') ? 1 : 0; }
+    const uintptr_t o0 = reinterpret_cast<uintptr_t>(p.out0);
+    p.epi_plain = !disable && p.out0 && p.out0_mode == 0 && p.out1_nsplit == 0 && !p.aux && !p.rowadd && g->N % 8 == 0 && p.ldo0 % 8 == 0 &&
+                  (o0 & (p.out0_dtype == PEA_F32 ? 31 : 15)) == 0 && (!p.bias || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
+  }
 
   if (pair) {
     const int pairs = p.total_tiles < num_sms() / 2 ? p.total_tiles : num_sms() / 2;
@@ -785,5 +881,5 @@ extern "C" int pea_gemm(const pea_gemm_desc* g, void* stream) {
   }
   const size_t smem = (size_t)stages * stage_bytes + 1024;
   const int ctas = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-  return dispatch(p, bn, ctas, smem, static_cast<cudaStream_t>(stream));
+  return dispatch(p, ctas, smem, static_cast<cudaStream_t>(stream));
 }

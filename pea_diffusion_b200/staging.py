@@ -57,6 +57,7 @@ class BatchStager:
             slot.copied.synchronize()      # this slot's previous upload has left its pinned buffers
         slot.keys = list(host_batch.keys())
         nbytes = 0
+        fresh = False
         for k, v in host_batch.items():
             if not isinstance(v, Tensor):
                 raise TypeError(f"batch[{k!r}] is {type(v).__name__}; only tensors are staged (keep text fields on the host)")
@@ -67,9 +68,14 @@ class BatchStager:
             if p is None or p.shape != v.shape or p.dtype != dt:
                 p = slot.pinned[k] = torch.empty(v.shape, dtype=dt).pin_memory()
                 slot.dev[k] = torch.empty(v.shape, dtype=dt, device=self.device)
+                fresh = True
             p.copy_(v)                     # host memcpy (+ cast) into the pinned slot
             nbytes += p.numel() * p.element_size()
         self.h2d_bytes = nbytes
+        if fresh:
+            # a new device buffer comes from the caching allocator of the CALLER's stream and may be memory that stream's
+            # pending work still uses: the first upload into it must be ordered after that work
+            self.copy_stream.wait_stream(torch.cuda.current_stream(self.device))
         if slot.consumed is not None:
             self.copy_stream.wait_event(slot.consumed)   # do not overwrite device buffers a step is still reading
         with torch.cuda.stream(self.copy_stream):

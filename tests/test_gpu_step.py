@@ -98,6 +98,19 @@ def test_config2_sdxl_full_shell_fused_vs_stock():
     assert float(dcs.abs().max()) > 0 and torch.isfinite(dcf).all()
 
 
+def test_config5_inference_fp16_full_shell_kv_cache():
+    """BASELINE.json configs[4] (tests/test_sdxl_zh.py:299-406) at full size: SDXL shell fp16, UNet batch 8 (4 prompts x CFG),
+    30 forward-only calls with a constant context.  The fused processors with the loop-invariant K|V cache must agree with the
+    stock processors after 30 accumulated steps, and project the context ONCE: 70 attention launches per call plus a single
+    all-layer projection GEMM for the whole loop."""
+    import bench
+    res = bench.infer_subrun(torch.device(DEV), steps=30)
+    print("config-5:", res)
+    assert res["rel_err_vs_stock_after_30_steps"] < 2e-2
+    assert res["stock"]["library_launches"] == 0
+    assert res["fused"]["library_launches"] == 30 * 70          # the timed loop re-uses the K|V of the warm-up loop: no GEMM at all
+
+
 def test_kd_loss_fp16_gradients_survive_with_loss_scale():
     """ADVICE r1 (kd_loss.py): in fp16 the unscaled feature-KD coefficient 0.1 * 2 / (numel * B) ~ 1e-8 is below the
     smallest subnormal; with the loss scale applied inside the fused pass (grad_prescale) the gradient matches the fp64

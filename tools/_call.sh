@@ -1,31 +1,27 @@
 mkdir -p gpurun_out/r2
-timeout 600 python -m pytest tests/test_gpu_step.py -x -q -k "dp_two" > gpurun_out/r2/gputests_2gpu.log 2>&1; echo "pytest rc=$?"
-tail -4 gpurun_out/r2/gputests_2gpu.log | cut -c1-300
-timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 5 --warmup 3 > gpurun_out/r2/bench_2gpu.json 2> gpurun_out/r2/bench_2gpu.err; echo "bench2 rc=$?"
-grep "bench \|Error\|error" gpurun_out/r2/bench_2gpu.err | tail -8 | cut -c1-300
+timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/r2/gputests.log 2>&1; echo "pytest rc=$?"
+tail -3 gpurun_out/r2/gputests.log | cut -c1-300
+PEA_GEMM_PLAIN_EPI=0 PEA_GEMM_BN=128 timeout 200 python tools/microbench.py --only gemm --iters 30 --out gpurun_out/r2/mb_gemm_old.jsonl > /dev/null 2>&1
+PEA_GEMM_BN=128 timeout 200 python tools/microbench.py --only gemm --iters 30 --out gpurun_out/r2/mb_gemm_plain128.jsonl > /dev/null 2>&1
+timeout 200 python tools/microbench.py --only gemm --iters 30 --out gpurun_out/r2/mb_gemm_new.jsonl > /dev/null 2>&1
+python - <<'PY'
+import json
+def load(f): return {d['name']:d for d in map(json.loads,open(f)) if d.get('op')=='gemm'}
+a,b,c=[load('gpurun_out/r2/mb_gemm_%s.jsonl'%v) for v in ('old','plain128','new')]
+for k in a: print('%-26s old(bn128,general epi) %.1f | bn128+plain epi %.1f | new %.1f | cublas %.1f'%(k,a[k]['us'],b[k]['us'],c[k]['us'],c[k]['cublas_us']))
+PY
+for cfg in "1024 1280" "4096 640"; do set -- $cfg; timeout 100 python tools/chain_probe.py --mode fwd --N $1 --C $2 --own-gemm 1 --pdl 1 2>/dev/null | python -c "
+import sys,json
+d=json.loads(sys.stdin.read()); print('own-gemm chain',d['N'],d['C'],'gemm pair per rep %.1f us, attn marginal %.2f'%(d['graph_without_us']/20,d['marginal_us_per_launch']))"; done
+timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/r2/bench3.json 2> gpurun_out/r2/bench3.err; echo "bench rc=$?"
 python - <<'PY'
 import json
 try:
-    d=json.loads(open('gpurun_out/r2/bench_2gpu.json').read().strip().splitlines()[-1])
-    print({k:d[k] for k in ('value','ms_per_step','n_gpus','gpu_launches','dp_params_identical','dp_param_checksums','loss')})
-    print('e2e',d['e2e']); print('strong',d['strong']); print(d['execution'])
+    d=json.loads(open('gpurun_out/r2/bench3.json').read().strip().splitlines()[-1])
+    print({k:d[k] for k in ('value','ms_per_step','gpu_launches','dp_params_identical')})
+    r=d['roofline']; print('roof',r['frac'],r['traffic_source']); print(r['in_chain_marginal'])
+    print({k:v['us_per_launch'] for k,v in r['per_kernel'].items()})
+    for row in r.get('sweep',[]): print(row['N'],row['C'],row['L'],row['fwd_us'],row['bwd_us'],row['fwd_frac'],row['bwd_frac'],row['fwdbwd_frac'])
+    for row in r.get('sweep_gemm',[]): print(row)
 except Exception as e: print('parse failed',e)
-PY
-# experimental: collectives captured in the graph (short leash)
-python - <<'PY'
-import os, subprocess, sys, re
-src=open('tests/test_gpu_step.py').read()
-m=re.search(r"_DP_NCCL_WORKER = r'''(.*?)'''", src, re.S)
-open('/tmp/dpw.py','w').write(m.group(1))
-procs=[]
-for r in range(2):
-    env=dict(os.environ, RANK=str(r), WORLD_SIZE='2', LOCAL_RANK=str(r), MASTER_ADDR='127.0.0.1', MASTER_PORT='29533')
-    procs.append(subprocess.Popen([sys.executable,'/tmp/dpw.py',os.getcwd(),'graphcap','fp32'],env=env,stdout=subprocess.PIPE,stderr=subprocess.STDOUT,text=True))
-for p in procs:
-    try:
-        out=p.communicate(timeout=150)[0]
-        print('graphcap rc',p.returncode, out[-400:].replace('\n',' | '))
-    except subprocess.TimeoutExpired:
-        for q in procs: q.kill()
-        print('graphcap TIMEOUT'); break
 PY

@@ -60,6 +60,9 @@ def main():
     def emit(**kw):
         print(json.dumps(kw)); out.write(json.dumps(kw) + "\n"); out.flush()
 
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from bench import ClockSampler          # nvidia-smi sampler shared with bench.py: clocks / throttle reasons under load
+    clocks = ClockSampler(0)
     dt = torch.bfloat16
     keep = [x for x in args.filter.split(",") if x]
     if not args.only or "attn" in args.only:
@@ -73,8 +76,7 @@ def main():
                     kv = torch.randn(B, L, 2 * C, device=DEV, dtype=dt)
                     do = torch.randn(B, N, C, device=DEV, dtype=dt)
                     d = C // H
-                    fb = 2 * B * N * C * 2 + 2 * B * L * C * 2
-                    bb = 3 * B * N * C * 2 + 2 * B * L * C * 2 + 2 * B * L * C * 4
+                    fb, bb = ops.attn2_bytes(B, N, L, C, 2)      # SURVEY.md section 8d formulas
                     tf, _ = timeit(lambda: ops.attn2_fwd(q, kv, H, d ** -0.5), args.iters)
                     tb, _ = timeit(lambda: ops.attn2_bwd(q, kv, do, H, d ** -0.5), args.iters)
                     # library: SDPA on [B,H,N,d] views (what AttnProcessor2_0 runs), fwd and fwd+bwd
@@ -126,6 +128,7 @@ def main():
         ops.TIMER.reset(False)
         emit(op="kd_mse", elems=sum(math.prod(x) for x in shp) + B * 4 * 128 * 128, us=s["ms"] / s["launches"] * 1e3,
              GBps=s["bytes"] / s["ms"] / 1e6, frac=s["bytes"] / s["ms"] / 1e6 / PEAK["hbm_gbs"])
+    emit(op="clocks", **clocks.stop())
 
 
 if __name__ == "__main__":

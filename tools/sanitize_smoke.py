@@ -4,7 +4,7 @@
     compute-sanitizer --tool memcheck python tools/sanitize_smoke.py
 
 Results are not checked here (tests/ does that); the point is out-of-bounds / misaligned accesses in the epilogues, the
-atomics and the TMA boxes at the edges.  Summary of the round-1 run: profiles/r1_sanitizer.txt.
+atomics and the TMA boxes at the edges.  Summaries: profiles/r1_sanitizer.txt, profiles/r2_sanitizer.txt.
 """
 import os
 import sys
@@ -41,6 +41,20 @@ for (B, N, L, H, d) in [(2, 1000, 52, 10, 64), (40, 100, 77, 20, 64), (1, 130, 8
         q, kv, do = rn(B, N, C, dt=dt), rn(B, L, 2 * C, dt=dt), rn(B, N, C, dt=dt)
         ops.attn2_fwd(q, kv, H, d ** -0.5)
         ops.attn2_bwd(q, kv, do, H, d ** -0.5)
+
+# programmatic dependent launch chain (round 2): to_q GEMM -> attn2 -> to_out GEMM with bias, all PEA_LAUNCH_PDL, and its backward
+B, N, L, H, d = 2, 300, 77, 4, 64
+C = H * d
+h, wq, wo, kv = rn(B * N, C), rn(C, C), rn(C, C), rn(B, L, 2 * C)
+bias = rn(C, dt=torch.float32)
+q = torch.empty(B * N, C, device=dev, dtype=torch.bfloat16)
+out = torch.empty(B * N, C, device=dev, dtype=torch.bfloat16)
+for _ in range(2):
+    ops.gemm([h], [wq], B * N, C, C, out0=q, pdl=True)
+    o = ops.attn2_fwd(q.view(B, N, C), kv, H, d ** -0.5, pdl=True)
+    ops.gemm([o.view(B * N, C)], [wo], B * N, C, C, bias=bias, out0=out, pdl=True)
+    ops.gemm([out], [wo], B * N, C, C, b_kmajor=False, out0=q, pdl=True)
+    dq, _ = ops.attn2_bwd(h.view(B, N, C), kv, q.view(B, N, C), H, d ** -0.5, pdl=True)
 
 # KD loss (ragged tap sizes), row ops
 shp = [(2, 4, 9, 9), (2, 320, 7, 5), (2, 1280, 3, 3)]

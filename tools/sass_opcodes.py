@@ -32,7 +32,7 @@ def main():
             continue
         if cur is None or "/*" not in line:
             continue
-        m = re.search(r"/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_.]*)", line)
+        m = re.search(r"/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_.]*)", line)
         if not m:
             continue
         kernels[cur]["instructions"] += 1
