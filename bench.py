@@ -485,6 +485,60 @@ def gemm_sweep(dev, iters=20, dtype=torch.bfloat16):
     return rows
 
 
+def adapter_subrun(dev, replays=20):
+    """The adapter alone at the step's size (M = 2 * 8 * 77 = 1232 rows, shipped 6.03 M MLP), forward + backward inside a CUDA
+    graph: this library's module (LayerNorm kernel + tcgen05 GEMM chain with fused GELU / GELU' / bias / pooling epilogues,
+    bf16 operands, fp32 master weights) against the same math in stock PyTorch under bf16 autocast (cuBLAS GEMMs + ATen
+    LayerNorm / GELU / mean kernels -- what the reference's `MLP` runs, train_sdxl_zh.py:58-67).  us per forward+backward."""
+    import torch.nn as nn
+    from pea_diffusion_b200 import adapter as A
+
+    class TorchMLP(nn.Module):      # the reference's module structure, restated (plain PyTorch baseline, not the oracle)
+        def __init__(self):
+            super().__init__()
+            self.layernorm = nn.LayerNorm(1024)
+            self.projector = nn.Sequential(nn.Linear(1024, 1024, bias=False), nn.GELU(), nn.Linear(1024, 1024, bias=False), nn.GELU(),
+                                           nn.Linear(1024, 1280, bias=False))
+            self.fc = nn.Linear(1280, 2048)
+
+        def forward(self, x):
+            x = self.projector(self.layernorm(x))
+            return torch.mean(x, 1), self.fc(nn.functional.gelu(x))
+
+    torch.manual_seed(0)
+    x = torch.randn(16, 77, 1024, device=dev)
+    res = {}
+    for name in ("library", "pytorch_bf16_autocast"):
+        m = (A.MLP(1024, 1280, 1024, 2048, False, precision="bf16") if name == "library" else TorchMLP()).to(dev)
+
+        def fb():
+            for p in m.parameters():
+                p.grad = None
+            if name == "library":
+                x1, x2 = m(x)
+            else:
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    x1, x2 = m(x)
+            (x1.float().sum() + x2.float().square().mean()).backward()
+
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                fb()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            fb()
+        res[name + "_us"] = time_replays(g, replays) * 1e3
+        del g
+    res["flops_fwd_bwd"] = 6 * 1232 * 6029312
+    res["library_TFLOPs"] = res["flops_fwd_bwd"] / res["library_us"] / 1e6
+    res["how"] = "CUDA-graph replay of one forward+backward (loss = sum(x1) + mean(x2^2)), median of %d, rows M = 1232" % replays
+    return res
+
+
 def infer_subrun(dev, steps=30):
     """BASELINE.json configs[4] (tests/test_sdxl_zh.py:299-406): SDXL shell fp16, UNet batch 8 (4 prompts x CFG), `steps`
     forward-only calls with a constant context; scheduler math replaced by `latents -= 0.01 * eps` (out of scope).
@@ -743,6 +797,7 @@ def main():
                 roof["in_chain_marginal"] = chain_marginal(dev, pk["hbm_gbs"])
                 roof["sweep"] = attn2_sweep(dev, pk["hbm_gbs"])
                 roof["sweep_gemm"] = gemm_sweep(dev)
+                roof["adapter_fwd_bwd"] = adapter_subrun(dev)
                 roof["sweep_how"] = ("each launch alone, 5 warm-up + 20 timed iterations, CUDA events on the launching stream, L2 flushed by "
                                      "reading 256 MB between iterations; median; fractions of the measured HBM peak")
             except Exception as exc:

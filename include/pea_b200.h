@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define PEA_B200_VERSION 100 /* 0.1.0 */
+#define PEA_B200_VERSION 200 /* 0.2.0: flags on the gemm / attn2 descriptors, inv_prescale on pea_kd_scale_grads */
 
 enum { PEA_OK = 0, PEA_EINVAL = -1, PEA_ECUDA = -2, PEA_ENODEV = -3, PEA_EUNSUPPORTED = -4 };
 /* `flags` of pea_gemm_desc / pea_attn2_desc.

@@ -29,6 +29,32 @@ from . import ops
 Tensor = torch.Tensor
 MAX_KEYS = 80
 _HEAD_DIMS = (40, 48, 64, 80, 160)
+PAD_SMALL_HEADS = True     # head_dim 40 / 48 (SD1.5's 320-channel blocks) run on the tcgen05 kernels, zero-padded to 64
+
+
+def _padded_head_dim(d: int) -> int:
+    """Head sizes below 64 are zero-padded to 64 IN THE FROZEN PROJECTION WEIGHTS (to_q / to_k / to_v get zero output rows,
+    to_out zero input columns), so q / k / v / o simply come out 64 wide per head and the head_dim-64 tcgen05 kernels serve
+    them: padded dims add 0 to q.k, produce 0 in o and meet zero columns of to_out.  The softmax scale stays d^-1/2."""
+    return 64 if (PAD_SMALL_HEADS and d < 64 and d % 8 == 0) else d
+
+
+def _pad_rows(w: Tensor, heads: int, d: int, dp: int) -> Tensor:
+    """[H*d, X] -> [H*dp, X]: every head's block of d output rows followed by dp - d zero rows."""
+    if dp == d:
+        return w
+    out = w.new_zeros(heads, dp, w.shape[1])
+    out[:, :d] = w.view(heads, d, w.shape[1])
+    return out.view(heads * dp, w.shape[1])
+
+
+def _pad_cols(w: Tensor, heads: int, d: int, dp: int) -> Tensor:
+    """[X, H*d] -> [X, H*dp]: zero input columns for the padded head dims."""
+    if dp == d:
+        return w
+    out = w.new_zeros(w.shape[0], heads, dp)
+    out[:, :, :d] = w.view(w.shape[0], heads, d)
+    return out.view(w.shape[0], heads * dp)
 
 
 class _Attn2Fn(torch.autograd.Function):
@@ -185,7 +211,9 @@ class Attn2Group:
 
     def __init__(self, attns):
         self.attns = list(attns)
-        self.widths = [2 * a.to_k.weight.shape[0] for a in self.attns]
+        self.dims = [(a.heads, a.to_k.weight.shape[0] // a.heads, _padded_head_dim(a.to_k.weight.shape[0] // a.heads)) if hasattr(a, "heads")
+                     else (1, a.to_k.weight.shape[0], a.to_k.weight.shape[0]) for a in self.attns]      # (H, d, padded d) per layer
+        self.widths = [2 * h * dp for (h, d, dp) in self.dims]
         self.offsets = [0]
         for w in self.widths[:-1]:
             self.offsets.append(self.offsets[-1] + w)
@@ -213,8 +241,8 @@ class Attn2Group:
                self.attns[0].to_k.weight.data_ptr())
         if self._wcat is None or self._wkey != key:
             parts = []
-            for a in self.attns:
-                parts += [a.to_k.weight.detach(), a.to_v.weight.detach()]
+            for a, (h, d, dp) in zip(self.attns, self.dims):
+                parts += [_pad_rows(a.to_k.weight.detach(), h, d, dp), _pad_rows(a.to_v.weight.detach(), h, d, dp)]
             self._wcat = torch.cat(parts, dim=0).to(device=device, dtype=dtype).contiguous()
             self._wkey = key
         return self._wcat
@@ -286,6 +314,8 @@ class PEAAttn2Processor:
         self.own_projections = own_projections
         self._bias32: Optional[Tensor] = None
         self._bias_key = None
+        self._pad_w = None          # (key, Wq padded [H*dp, C], Wo padded [C, H*dp]) for head sizes below 64
+
         self._wkv: Optional[Tensor] = None
         self._wkv_key = None
         self._kv: Optional[Tensor] = None
@@ -317,6 +347,20 @@ class PEAAttn2Processor:
                 self._bias32, self._bias_key = lin.bias.detach().float().contiguous(), key
             b32 = self._bias32
         return _FrozenLinearFn.apply(x, w.detach(), b32)
+
+    def _padded_projections(self, attn, dt, d: int, dp: int):
+        """Zero-padded copies of the frozen to_q / to_out[0] weights (built once per weight version), or None when those
+        modules are not plain frozen Linears -- then the layer keeps its true head size and the warp-MMA kernels."""
+        lq, lo = attn.to_q, attn.to_out[0]
+        for lin in (lq, lo):
+            if getattr(lin, "lora_layer", None) is not None or lin.weight.dtype != dt or \
+                    (torch.is_grad_enabled() and (lin.weight.requires_grad or (lin.bias is not None and lin.bias.requires_grad))):
+                return None
+        key = (lq.weight.data_ptr(), lq.weight._version, lo.weight.data_ptr(), lo.weight._version, dt)
+        if self._pad_w is None or self._pad_w[0] != key:
+            self._pad_w = (key, _pad_rows(lq.weight.detach(), attn.heads, d, dp).contiguous(),
+                           _pad_cols(lo.weight.detach(), attn.heads, d, dp).contiguous())
+        return self._pad_w[1], self._pad_w[2]
 
     def _supported(self, attn, hidden_states, encoder_hidden_states, attention_mask) -> bool:
         if encoder_hidden_states is None or attention_mask is not None:
@@ -350,16 +394,29 @@ class PEAAttn2Processor:
             return self.fallback(attn, hidden_states, encoder_hidden_states=encoder_hidden_states,
                                  attention_mask=attention_mask, temb=temb, scale=scale)
         dt = hidden_states.dtype
-        q = self._linear(attn.to_q, hidden_states, scale, False)
-        if self.group is not None and id(attn) in self.group.index and self.group.supported(dt):
+        d = attn.to_q.weight.shape[0] // attn.heads
+        dp = _padded_head_dim(d)
+        pad = self._padded_projections(attn, dt, d, dp) if dp != d else None
+        grouped = self.group is not None and id(attn) in self.group.index and self.group.supported(dt)
+        if dp != d and (pad is None or not grouped):
+            dp, pad = d, None          # per-layer path / non-plain projections: true head size (warp-MMA kernels)
+            grouped = grouped and self.group.dims[self.group.index[id(attn)]][2] == d
+        if pad is not None:
+            q = torch.nn.functional.linear(hidden_states, pad[0])      # [B, N, H * 64]: the padded dims are exact zeros
+        else:
+            q = self._linear(attn.to_q, hidden_states, scale, False)
+        if grouped:
             # all layers' K|V from ONE projection GEMM per forward pass (and per denoise loop when the context is reused)
             B, L, _ = encoder_hidden_states.shape
             i = self.group.index[id(attn)]
             kv_all, token = self.group.project(encoder_hidden_states, dt, i)
             off, c2 = self.group.offsets[i], self.group.widths[i]
             kv = kv_all.view(B, L, self.group.total)[:, :, off:off + c2]
-            o = _Attn2GroupedFn.apply(q, token, kv, self.group, i, attn.heads, float(attn.scale), self.own_projections)
-            o = self._linear(attn.to_out[0], o, scale, True)
+            o = _Attn2GroupedFn.apply(q, token, kv, self.group, i, attn.heads, float(attn.scale), self.own_projections and pad is None)
+            if pad is not None:
+                o = torch.nn.functional.linear(o, pad[1], attn.to_out[0].bias)
+            else:
+                o = self._linear(attn.to_out[0], o, scale, True)
             return attn.to_out[1](o)
         context = encoder_hidden_states.to(dt)
         if not context.is_contiguous():

@@ -7,13 +7,14 @@
 //             fp32-accurate mode all live in the epilogue;
 //           * attn2's to_k / to_v projections of the context (diffusers AttnProcessor2_0) and dContext = dK Wk + dV Wv.
 //
-// Structure (persistent CTAs, 128 x BN output tiles with BN = 128 or 256, 192 threads):
+// Structure (persistent CTAs, 128 x bn output tiles, bn a multiple of 16 chosen per problem against the wave count, 320 threads):
 //   warp 0      TMA producer: 128B-swizzled [128 x 64] / [BN x 64] operand tiles, `stages`-deep mbarrier ring that runs
 //               across tile boundaries
 //   warp 1      TMEM allocator + MMA issuer: one elected lane issues tcgen05.mma (M128 N{128,256} K16, kind::f16, fp32
 //               accumulate); accumulators are DOUBLE BUFFERED in TMEM (2 x BN columns) so tile i+1's main loop runs
 //               while the epilogue drains tile i; tcgen05.commit releases smem stages and signals the epilogue
-//   warps 2..5  epilogue: tcgen05.ld (each warp its 32-lane TMEM quadrant, thread = output row), fused math, stores
+//   warps 2..9  epilogue: tcgen05.ld (each warp its 32-lane TMEM quadrant, thread = output row; two warps per quadrant, half
+//               the tile's columns each), fused math, stores
 // Operand majors: K-major tiles come from one {64, 128} TMA box; MN-major tiles (A^T / B^T stored row-major) from two
 // {64, 64} boxes, consumed through MN-major UMMA descriptors -- so dX = dY W and dW = dY^T X need no transposes.
 // fp32-accurate mode: operands are sums of up to 3 bf16 planes; per K step the kernel issues the cross products
@@ -32,7 +33,9 @@ namespace {
 constexpr int BM = 128, BK = 64;
 constexpr int kTileBytes = BM * BK * 2;  // 16 KiB per 128-row operand plane per stage
 constexpr int kMaxStages = 8;
-constexpr int kThreads = 192;
+constexpr int kThreads = 192;        // gemm_tc2_kernel (CTA pairs): producer, MMA issuer, 4 epilogue warps
+constexpr int kThreads1 = 320;       // gemm_tc_kernel: producer, MMA issuer, 8 epilogue warps (two per TMEM lane quadrant, half the
+                                     // tile's columns each: a one-wave GEMM's epilogue is fully exposed, so its latency is halved)
 constexpr size_t kSmemBudget = 208 * 1024;
 
 struct GemmParams {
@@ -306,7 +309,7 @@ __device__ unsigned long long g_trace_gemm[64];
 // elected lane.  A single-lane loop with runtime plane / major branches measured ~430 cycles between MMAs (the
 // 128x128x16 MMA itself takes 64): r1 ncu capture profiles/gemm_r1_before.txt.
 template <int SA, int SB, int A_MN, int B_MN>
-__global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
+__global__ void __launch_bounds__(kThreads1, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
@@ -343,7 +346,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       tc::mbar_init(smem_u32(&empty_bar[s]), 1);
     }
     tc::mbar_init(smem_u32(&acc_full[0]), 1); tc::mbar_init(smem_u32(&acc_full[1]), 1);
-    tc::mbar_init(smem_u32(&acc_empty[0]), 4); tc::mbar_init(smem_u32(&acc_empty[1]), 4);
+    tc::mbar_init(smem_u32(&acc_empty[0]), 8); tc::mbar_init(smem_u32(&acc_empty[1]), 8);
     tc::fence_mbar_init();
   }
   if (warp == 1) tc::tmem_alloc(smem_u32(&tmem_base_slot), kTmemCols);
@@ -451,7 +454,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       tc::mbar_wait(smem_u32(&acc_full[as]), (uint32_t)(local >> 1) & 1u);
       if (local == 0 && warp == 2) GTRACE(4);              // first accumulator complete
       tc::fence_after_sync();
-      epilogue_tile(p, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)as * kAccStride, m0 + q * 32 + lane, n0, bn, al0, al1, alx);
+      // warps 2-5 take the tile's first bn / 2 columns, warps 6-9 the rest (bn is a multiple of 16, so both halves are
+      // multiples of 8 columns)
+      const int half = (warp - 2) >> 2, hw = bn >> 1;
+      epilogue_tile(p, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)as * kAccStride + (uint32_t)(half * hw), m0 + q * 32 + lane,
+                    n0 + half * hw, hw, al0, al1, alx);
       if (local == 0 && warp == 2) GTRACE(5);              // first tile's epilogue done (this warp)
       tc::fence_before_sync();
       __syncwarp();
@@ -624,7 +631,7 @@ template <int SA, int SB, int A_MN, int B_MN>
 int launch(const GemmParams& p, int ctas, size_t smem, cudaStream_t st) {
   static std::atomic<unsigned long long> attr_done{0};
   if (int rc = ensure_dynamic_smem(gemm_tc_kernel<SA, SB, A_MN, B_MN>, (int)(kSmemBudget + 1024), attr_done)) return rc;
-  PEA_CUDA(launch_ex(gemm_tc_kernel<SA, SB, A_MN, B_MN>, ctas, kThreads, smem, st, p.pdl != 0, p));
+  PEA_CUDA(launch_ex(gemm_tc_kernel<SA, SB, A_MN, B_MN>, ctas, kThreads1, smem, st, p.pdl != 0, p));
   PEA_LAUNCH_CHECK();
   return PEA_OK;
 }
@@ -776,7 +783,8 @@ extern "C" int pea_gemm(const pea_gemm_desc* g, void* stream) {
   p.a_mn = g->a_kmajor ? 0 : 1; p.b_mn = g->b_kmajor ? 0 : 1;
   const bool fp16 = g->in_dtype == PEA_F16;
   // Tile width: the multiple of 16 in [32, 256] that minimises  waves x (K blocks x time per stage + epilogue)  with
-  //   time per stage = max(MMA: 2 bn clk per plane product, feed: stage bytes / ~60 B per clk of L2 -> shared memory per SM).
+  //   time per stage = max(MMA: 2 bn clk per plane product, feed: stage bytes / ~48 B per clk of L2 -> shared memory per SM;
+  //   calibrated on the 128 x 256 tile: 1 010 clk per K block at 4096^3).
   // Wide tiles halve the A re-reads and raise the tensor duty under the shared-memory bandwidth bound, but a one-wave
   // problem wants as many CTAs as fit in ONE wave: M = 1232, N = 2048 ran 160 tiles of 128 x 128 on 148 SMs -- twelve CTAs did
   // two -- and now runs 130 tiles of 128 x 160 (profiles/r2_gemm_timeline.txt).  PEA_GEMM_BN forces a width (A/B runs).
@@ -795,23 +803,28 @@ extern "C" int pea_gemm(const pea_gemm_desc* g, void* stream) {
       if (kSmemBudget / stage < 2) continue;                       // needs at least a double buffer
       const long long tiles = (long long)m_tiles * ((g->N + cand - 1) / cand) * nsplit_k;
       const double waves = (double)((tiles + sms - 1) / sms);
-      const double t_stage = fmax(2.0 * cand * nprod, (double)stage / 60.0);
+      const double t_stage = fmax(2.0 * cand * nprod, (double)stage / 48.0);
       const double cost = waves * ((double)((kb_all + nsplit_k - 1) / nsplit_k) * t_stage + 12.0 * cand);
       if (cost < best * 0.999) { best = cost; bn = cand; }
     }
     if (forced >= 32 && forced <= 256 && forced % 16 == 0) bn = forced;
   }
-  // CTA pairs (256 x 256 per two SMs) when there is a pair tile per SM pair and the row padding to 256 does not eat the
-  // gain (measured: 1 329 vs 1 169 TF/s at 4096^3, x1.14; at M = 616 the 768-row padding loses: 895 vs 1 031 TF/s);
-  // PEA_GEMM_PAIR=0/1 forces the choice for A/B runs.
+  // CTA pairs (256 x 256 per two SMs) when there is a pair tile per SM pair, the row padding to 256 does not eat the gain
+  // (measured: 1 329 vs 1 169 TF/s at 4096^3, x1.14; at M = 616 the 768-row padding loses: 895 vs 1 031 TF/s) AND the pair
+  // tiles fill their last wave to >= 80 % (8192 x 1280 x 1280: 160 pair tiles on 74 pairs = 2.16 waves cost 37.8 us, the
+  // searched 128 x 224 tiles 28 us).  PEA_GEMM_PAIR=0/1 forces the choice for A/B runs.
   bool pair = false;
-  if (bn == 256 && p.sa == 1 && p.sb == 1 && g->split_k <= 1) {   // the pair kernel is single-plane, no split-K
+  if (p.sa == 1 && p.sb == 1 && g->split_k <= 1) {   // the pair kernel is single-plane, no split-K
     const long long pm = (g->M + 255) / 256, pn = (g->N + 255) / 256;
+    const int npairs = num_sms() / 2;
     const double eff_pair = (double)g->M / (256.0 * pm), eff_single = (double)g->M / (128.0 * m_tiles);
-    pair = pm * pn >= num_sms() / 2 && eff_pair * 1.12 > eff_single;
+    const double wave_eff = (double)(pm * pn) / (double)(((pm * pn + npairs - 1) / npairs) * npairs);
+    const double col_eff = (double)g->N / (256.0 * pn);     // N = 640 pads to 768 columns: 17 % of every pair tile wasted
+    pair = pm * pn >= npairs && eff_pair * 1.12 > eff_single && wave_eff * col_eff >= 0.8;
     static int forced = -2;
     if (forced == -2) { const char* e = getenv("PEA_GEMM_PAIR"); forced = e ? atoi(e) : -1; }
     if (forced >= 0) pair = forced != 0;
+    if (pair) bn = 256;
   }
   for (int i = 0; i < p.sa; ++i) {
     PEA_CHECK_ARG(g->d_A[i] && (reinterpret_cast<uintptr_t>(g->d_A[i]) & 15) == 0, "gemm: A plane %d null or not 16-byte aligned", i);

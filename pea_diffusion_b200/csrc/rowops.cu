@@ -3,8 +3,11 @@
 //   torch.mean(x, 1)                       train_sdxl_zh.py:66
 //   where(prompt_mask, uncond, cond)       train_sdxl_zh.py:392-395
 // plus operand splitting (fp32 -> bf16 planes) for the fp32-accurate GEMM mode and the bias/affine gradients.
-// All of these touch <= a few MB per step (M = 2*B*77 rows); they are written for clarity and determinism
-// (fixed-order reductions, no float atomics), not tuned.
+// All of these touch <= a few MB per step (M = 2*B*77 rows) -- except the plane split of the all-layer dK|dV accumulator
+// (410 MB).  Round 2: the ncu launch list of a step (profiles/r2_launches_step_graph.txt) showed them costing a third of the
+// adapter's forward+backward (LayerNorm backward 38 us on 32 CTAs, column sum 20 us, LayerNorm forward 20 us, 7-12 us per
+// weight cast with a 64-bit division per element), so the hot ones got vectorised / row-parallel forms.  The affine and
+// bias gradients are now reduced with fp32 atomics over row chunks (order-dependent in the last bits, like dK / dV).
 #include "common.cuh"
 
 namespace pea {
@@ -64,15 +67,54 @@ __global__ void layernorm_fwd_kernel(const void* __restrict__ x, pea_dtype xdt, 
   if (lane == 0) { mean_out[row] = mean; rstd_out[row] = rstd; }
 }
 
-// dgamma[d] += sum_m dy*xhat ; dbeta[d] += sum_m dy.  block (32, 8): 32 columns, rows strided over y; fixed order.
+// Same, fp32 rows with D = 128 * NV (<= 2048): the row is read ONCE with 128-bit loads and stays in registers for the mean,
+// the variance and the normalised output (the general kernel above makes three latency-bound passes of scalar loads).
+template <int NV>
+__global__ void layernorm_fwd_vec_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                         int M, float eps, Planes y, int nsplit, pea_dtype pdt, float* __restrict__ mean_out,
+                                         float* __restrict__ rstd_out) {
+  constexpr int D = NV * 128;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + (long long)row * D);
+  float4 v[NV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) { v[i] = xr[i * 32 + lane]; s += (v[i].x + v[i].y) + (v[i].z + v[i].w); }
+  const float mean = warp_sum(s) / (float)D;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    q += (a * a + b * b) + (c * c + d * d);
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (float)D + eps);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c0 = (i * 32 + lane) * 4;
+    const float4 g = *reinterpret_cast<const float4*>(gamma + c0), b = *reinterpret_cast<const float4*>(beta + c0);
+    const long long base = (long long)row * D + c0;
+    store_split(y, nsplit, pdt, base + 0, fmaf((v[i].x - mean) * rstd, g.x, b.x));
+    store_split(y, nsplit, pdt, base + 1, fmaf((v[i].y - mean) * rstd, g.y, b.y));
+    store_split(y, nsplit, pdt, base + 2, fmaf((v[i].z - mean) * rstd, g.z, b.z));
+    store_split(y, nsplit, pdt, base + 3, fmaf((v[i].w - mean) * rstd, g.w, b.w));
+  }
+  if (lane == 0) { mean_out[row] = mean; rstd_out[row] = rstd; }
+}
+
+// dgamma[d] += sum_m dy*xhat ; dbeta[d] += sum_m dy.  block (32, 8): 32 columns; grid.y chunks of rows, each chunk's partial
+// sums added with one fp32 atomic per column (the caller zero-fills or really accumulates).
 __global__ void layernorm_bwd_affine_kernel(const void* __restrict__ x, pea_dtype xdt, const float* __restrict__ dy,
                                             const float* __restrict__ mean, const float* __restrict__ rstd, int M, int D,
                                             float* __restrict__ dgamma, float* __restrict__ dbeta) {
   __shared__ float sg[8][33], sb[8][33];
   const int col = blockIdx.x * 32 + threadIdx.x;
+  const int rows_per = (M + gridDim.y - 1) / gridDim.y;
+  const int m_begin = blockIdx.y * rows_per, m_end = min(M, m_begin + rows_per);
   float ag = 0.f, ab = 0.f;
   if (col < D) {
-    for (int m = threadIdx.y; m < M; m += 8) {
+    for (int m = m_begin + threadIdx.y; m < m_end; m += 8) {
       const float g = dy[(long long)m * D + col];
       const float xh = (load_any(x, xdt, (long long)m * D + col) - mean[m]) * rstd[m];
       ag = fmaf(g, xh, ag);
@@ -86,8 +128,8 @@ __global__ void layernorm_bwd_affine_kernel(const void* __restrict__ x, pea_dtyp
     float tg = 0.f, tb = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) { tg += sg[i][threadIdx.x]; tb += sb[i][threadIdx.x]; }
-    dgamma[col] += tg;
-    dbeta[col] += tb;
+    atomicAdd(dgamma + col, tg);
+    atomicAdd(dbeta + col, tb);
   }
 }
 
@@ -125,34 +167,78 @@ __global__ void split_planes_kernel(const void* __restrict__ x, pea_dtype xdt, l
   }
 }
 
+// Contiguous fp32 source (ld == cols, 32-byte aligned, n % 8 == 0): 8 elements per thread per step, 128-bit loads, one
+// 128-bit store per plane, no index arithmetic beyond the grid stride.
+__global__ void split_planes_vec_kernel(const float* __restrict__ x, long long n8, Planes pl, int nsplit, pea_dtype pdt) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    const float4 a = reinterpret_cast<const float4*>(x)[2 * i], b = reinterpret_cast<const float4*>(x)[2 * i + 1];
+    float r[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+      if (s < nsplit) {
+        uint4 u;
+        if (pdt == PEA_F16) {
+          u = make_uint4(pack2<__half>(r[0], r[1]), pack2<__half>(r[2], r[3]), pack2<__half>(r[4], r[5]), pack2<__half>(r[6], r[7]));
+          if (s + 1 < nsplit) {
+            const float2 q0 = unpack2<__half>(u.x), q1 = unpack2<__half>(u.y), q2 = unpack2<__half>(u.z), q3 = unpack2<__half>(u.w);
+            r[0] -= q0.x; r[1] -= q0.y; r[2] -= q1.x; r[3] -= q1.y; r[4] -= q2.x; r[5] -= q2.y; r[6] -= q3.x; r[7] -= q3.y;
+          }
+        } else {
+          u = make_uint4(pack2<__nv_bfloat16>(r[0], r[1]), pack2<__nv_bfloat16>(r[2], r[3]), pack2<__nv_bfloat16>(r[4], r[5]),
+                         pack2<__nv_bfloat16>(r[6], r[7]));
+          if (s + 1 < nsplit) {
+            const float2 q0 = unpack2<__nv_bfloat16>(u.x), q1 = unpack2<__nv_bfloat16>(u.y), q2 = unpack2<__nv_bfloat16>(u.z),
+                         q3 = unpack2<__nv_bfloat16>(u.w);
+            r[0] -= q0.x; r[1] -= q0.y; r[2] -= q1.x; r[3] -= q1.y; r[4] -= q2.x; r[5] -= q2.y; r[6] -= q3.x; r[7] -= q3.y;
+          }
+        }
+        reinterpret_cast<uint4*>(pl.p[s])[i] = u;
+      }
+    }
+  }
+}
+
 __global__ void mean_tokens_kernel(const float* __restrict__ x, const void* __restrict__ res, pea_dtype rdt, int L, int D,
                                    float* __restrict__ out) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   const int b = blockIdx.y;
   if (n >= D) return;
-  float s = 0.f;
-  for (int l = 0; l < L; ++l) {
-    const long long i = ((long long)b * L + l) * D + n;
+  float s4[4] = {0.f, 0.f, 0.f, 0.f};      // four loads in flight (one serial chain of 77 dependent adds took 9 us)
+  const long long base = (long long)b * L * D + n;
+  int l = 0;
+  for (; l + 4 <= L; l += 4) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const long long i = base + (long long)(l + j) * D;
+      float v = x[i];
+      if (res) v += load_any(res, rdt, i);
+      s4[j] += v;
+    }
+  }
+  for (; l < L; ++l) {
+    const long long i = base + (long long)l * D;
     float v = x[i];
     if (res) v += load_any(res, rdt, i);
-    s += v;
+    s4[0] += v;
   }
-  out[(long long)b * D + n] = s / (float)L;
+  out[(long long)b * D + n] = ((s4[0] + s4[1]) + (s4[2] + s4[3])) / (float)L;
 }
 
 __global__ void colsum_accum_kernel(const void* __restrict__ x, pea_dtype xdt, int M, int N, long long ld, float* __restrict__ out) {
   __shared__ float sm[8][33];
   const int col = blockIdx.x * 32 + threadIdx.x;
+  const int rows_per = (M + gridDim.y - 1) / gridDim.y;
+  const int m_begin = blockIdx.y * rows_per, m_end = min(M, m_begin + rows_per);
   float a = 0.f;
   if (col < N)
-    for (int m = threadIdx.y; m < M; m += 8) a += load_any(x, xdt, (long long)m * ld + col);
+    for (int m = m_begin + threadIdx.y; m < m_end; m += 8) a += load_any(x, xdt, (long long)m * ld + col);
   sm[threadIdx.y][threadIdx.x] = a;
   __syncthreads();
   if (threadIdx.y == 0 && col < N) {
     float t = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) t += sm[i][threadIdx.x];
-    out[col] += t;
+    atomicAdd(out + col, t);
   }
 }
 
@@ -210,8 +296,17 @@ extern "C" int pea_layernorm_fwd(const void* d_x, pea_dtype x_dtype, const float
   PEA_CHECK_ARG(plane_dtype != PEA_F32, "layernorm_fwd: planes are 16-bit");
   Planes pl{};
   for (int s = 0; s < nsplit; ++s) { PEA_CHECK_ARG(d_y_planes[s], "layernorm_fwd: null plane %d", s); pl.p[s] = d_y_planes[s]; }
-  layernorm_fwd_kernel<<<(M + 3) / 4, 128, 0, (cudaStream_t)stream>>>(d_x, x_dtype, d_gamma, d_beta, M, D, eps, pl, nsplit,
-                                                                    plane_dtype, d_mean, d_rstd);
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  const bool vec = x_dtype == PEA_F32 && D % 128 == 0 && D <= 2048 && al16(d_x) && al16(d_gamma) && al16(d_beta);
+  cudaStream_t st = (cudaStream_t)stream;
+  const float* xf = static_cast<const float*>(d_x);
+#define PEA_LN_VEC(NV) layernorm_fwd_vec_kernel<NV><<<(M + 3) / 4, 128, 0, st>>>(xf, d_gamma, d_beta, M, eps, pl, nsplit, plane_dtype, d_mean, d_rstd)
+  if (vec && D == 1024) PEA_LN_VEC(8);
+  else if (vec && D == 768) PEA_LN_VEC(6);
+  else if (vec && D == 2048) PEA_LN_VEC(16);
+  else if (vec && D == 128) PEA_LN_VEC(1);
+  else layernorm_fwd_kernel<<<(M + 3) / 4, 128, 0, st>>>(d_x, x_dtype, d_gamma, d_beta, M, D, eps, pl, nsplit, plane_dtype, d_mean, d_rstd);
+#undef PEA_LN_VEC
   PEA_LAUNCH_CHECK();
   return PEA_OK;
 }
@@ -220,8 +315,13 @@ extern "C" int pea_layernorm_bwd(const void* d_x, pea_dtype x_dtype, const float
                                  const float* d_rstd, int M, int D, float* d_dgamma, float* d_dbeta, float* d_dx, void* stream) {
   PEA_CHECK_ARG(d_x && d_dy && d_gamma && d_mean && d_rstd && d_dgamma && d_dbeta, "layernorm_bwd: null pointer");
   PEA_CHECK_ARG(M >= 1 && D >= 1, "layernorm_bwd: bad M/D");
-  layernorm_bwd_affine_kernel<<<(D + 31) / 32, dim3(32, 8), 0, (cudaStream_t)stream>>>(d_x, x_dtype, d_dy, d_mean, d_rstd, M, D,
-                                                                                    d_dgamma, d_dbeta);
+  // enough row chunks to cover the machine (D = 1024: 32 column blocks x 8 row chunks); at least 64 rows per chunk
+  const int cb = (D + 31) / 32;
+  int rc = (2 * num_sms() + cb - 1) / cb;
+  if (rc > (M + 63) / 64) rc = (M + 63) / 64;
+  if (rc < 1) rc = 1;
+  layernorm_bwd_affine_kernel<<<dim3(cb, rc), dim3(32, 8), 0, (cudaStream_t)stream>>>(d_x, x_dtype, d_dy, d_mean, d_rstd, M, D,
+                                                                                   d_dgamma, d_dbeta);
   PEA_LAUNCH_CHECK();
   if (d_dx) {
     layernorm_bwd_dx_kernel<<<(M + 3) / 4, 128, 0, (cudaStream_t)stream>>>(d_x, x_dtype, d_dy, d_gamma, d_mean, d_rstd, M, D, d_dx);
@@ -237,6 +337,15 @@ extern "C" int pea_split_planes(const void* d_x, pea_dtype x_dtype, long long ro
   Planes pl{};
   for (int s = 0; s < nsplit; ++s) { PEA_CHECK_ARG(d_planes[s], "split_planes: null plane %d", s); pl.p[s] = d_planes[s]; }
   const long long n = rows * cols;
+  bool vec = x_dtype == PEA_F32 && ld == cols && n % 8 == 0 && (reinterpret_cast<uintptr_t>(d_x) & 31) == 0;
+  for (int s = 0; s < nsplit; ++s) vec = vec && (reinterpret_cast<uintptr_t>(d_planes[s]) & 15) == 0;
+  if (vec) {
+    const long long n8 = n / 8;
+    const int grid = (int)((n8 + 255) / 256 < (long long)num_sms() * 16 ? (n8 + 255) / 256 : (long long)num_sms() * 16);
+    split_planes_vec_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(static_cast<const float*>(d_x), n8, pl, nsplit, plane_dtype);
+    PEA_LAUNCH_CHECK();
+    return PEA_OK;
+  }
   const int grid = (int)((n + 255) / 256 < (long long)num_sms() * 16 ? (n + 255) / 256 : (long long)num_sms() * 16);
   split_planes_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_x, x_dtype, rows, cols, ld, pl, nsplit, plane_dtype);
   PEA_LAUNCH_CHECK();
@@ -253,7 +362,11 @@ extern "C" int pea_mean_tokens(const float* d_x, const void* d_res, pea_dtype re
 
 extern "C" int pea_colsum_accum(const void* d_x, pea_dtype x_dtype, int M, int N, long long ld, float* d_out, void* stream) {
   PEA_CHECK_ARG(d_x && d_out && M >= 1 && N >= 1 && ld >= N, "colsum_accum: bad arguments");
-  colsum_accum_kernel<<<(N + 31) / 32, dim3(32, 8), 0, (cudaStream_t)stream>>>(d_x, x_dtype, M, N, ld, d_out);
+  const int cb = (N + 31) / 32;
+  int rc = (2 * num_sms() + cb - 1) / cb;
+  if (rc > (M + 63) / 64) rc = (M + 63) / 64;
+  if (rc < 1) rc = 1;
+  colsum_accum_kernel<<<dim3(cb, rc), dim3(32, 8), 0, (cudaStream_t)stream>>>(d_x, x_dtype, M, N, ld, d_out);
   PEA_LAUNCH_CHECK();
   return PEA_OK;
 }

@@ -111,6 +111,34 @@ def test_config5_inference_fp16_full_shell_kv_cache():
     assert res["fused"]["library_launches"] == 30 * 70          # the timed loop re-uses the K|V of the warm-up loop: no GEMM at all
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_sd15_head_dim_40_runs_on_tcgen05_kernels_via_zero_padding(dtype):
+    """SD1.5's 320-channel blocks (8 heads x 40, N = 1024 at 256 px: train_sd_zh.py:215, tests/test_sd_zh.py:202): with the
+    grouped projection the frozen to_q / to_k / to_v / to_out weights are zero-padded to head_dim 64, so the head_dim-64 tcgen05
+    kernels serve the layer; the whole module and its gradients still match the oracle's AttnProcessor2_0 restatement."""
+    from oracle import pea_oracle as O
+    from pea_diffusion_b200.attn2 import Attn2Group, PEAAttn2Processor
+    from pea_diffusion_b200.shell.unet import Attention, StockAttnProcessor
+    torch.manual_seed(0)
+    B, N, L, C, H, Dc = 2, 1024, 77, 320, 8, 768
+    attn = Attention(C, Dc, H, C // H)
+    h, ctx, gout = torch.randn(B, N, C), torch.randn(B, L, Dc), torch.randn(B, N, C)
+    rnd = lambda t: t.detach().to(dtype).float()
+    hf, cf = rnd(h).requires_grad_(True), rnd(ctx).requires_grad_(True)
+    ref = O.attn2(hf, cf, rnd(attn.to_q.weight), rnd(attn.to_k.weight), rnd(attn.to_v.weight), rnd(attn.to_out[0].weight),
+                  rnd(attn.to_out[0].bias), H)
+    ref.backward(rnd(gout))
+    attn = attn.to(device=DEV, dtype=dtype).requires_grad_(False)
+    group = Attn2Group([attn])
+    assert group.dims == [(8, 40, 64)] and group.widths == [2 * 8 * 64]
+    attn.set_processor(PEAAttn2Processor(fallback=StockAttnProcessor(), group=group))
+    hd = h.to(device=DEV, dtype=dtype).requires_grad_(True)
+    cd = ctx.to(device=DEV, dtype=dtype).requires_grad_(True)
+    out = attn(hd, encoder_hidden_states=cd)
+    out.backward(gout.to(device=DEV, dtype=dtype))
+    assert rel_err(out, ref) < 2e-2 and rel_err(hd.grad, hf.grad) < 2e-2 and rel_err(cd.grad, cf.grad) < 2e-2
+
+
 def test_kd_loss_fp16_gradients_survive_with_loss_scale():
     """ADVICE r1 (kd_loss.py): in fp16 the unscaled feature-KD coefficient 0.1 * 2 / (numel * B) ~ 1e-8 is below the
     smallest subnormal; with the loss scale applied inside the fused pass (grad_prescale) the gradient matches the fp64
