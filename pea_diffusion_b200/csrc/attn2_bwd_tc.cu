@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_bwd_tc_kernel(const __grid_
           __syncwarp();
           ++kv_n;
         }
-        tc::mbar_wait(smem_u32(&ring_empty[s]), ring_ph ^ 1u);
+        if (t >= kRing) tc::mbar_wait(smem_u32(&ring_empty[s]), ring_ph ^ 1u);   // the first ring pass is free
         TRACE(0, t, 0);
         if (tc::elect_one()) {
           const uint32_t fb = smem_u32(&ring_full[s]);

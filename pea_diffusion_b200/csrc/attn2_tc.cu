@@ -184,8 +184,8 @@ __global__ void __launch_bounds__(kThreads, 1) attn2_fwd_tc_kernel(const __grid_
         ++kv_n;
       }
       const int s = t % kQStages;
-      tc::mbar_wait(smem_u32(&q_empty[s]), ((uint32_t)(t / kQStages) & 1u) ^ 1u);
-      TRACE(0, t, 0);
+      if (t >= kQStages) tc::mbar_wait(smem_u32(&q_empty[s]), ((uint32_t)(t / kQStages) & 1u) ^ 1u);   // the first ring pass is free:
+      TRACE(0, t, 0);                                                                                  // no ~100-clk try_wait per start-up load
       if (tc::elect_one()) {
         const uint32_t fb = smem_u32(&q_full[s]);
         tc::mbar_expect_tx(fb, kQBytes);

@@ -1,15 +1,17 @@
 mkdir -p gpurun_out/r2
-timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/r2/gputests.log 2>&1; echo "pytest rc=$?"
-tail -3 gpurun_out/r2/gputests.log | cut -c1-300
-timeout 200 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1 | cut -c1-400
-timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/r2/bench5.json 2> gpurun_out/r2/bench5.err; echo "bench rc=$?"
+T=build/variants
+timeout 300 python -m pytest tests/test_gpu_parity.py -x -q -k "attn2" 2>&1 | tail -2
+PEA_B200_LIB=$T/libpea_nopf.so timeout 200 python tools/microbench.py --only attn --iters 30 --out gpurun_out/r2/mb_nopf.jsonl > /dev/null 2>&1
+timeout 200 python tools/microbench.py --only attn --iters 30 --out gpurun_out/r2/mb_pf.jsonl > /dev/null 2>&1
 python - <<'PY'
 import json
-try:
-    d=json.loads(open('gpurun_out/r2/bench5.json').read().strip().splitlines()[-1])
-    print({k:d[k] for k in ('value','ms_per_step','gpu_launches','dp_params_identical')})
-    r=d['roofline']; print('roof',r['frac']); print(r['in_chain_marginal']['step_mix']); print(r.get('adapter_fwd_bwd'))
-    print({k:v['us_per_launch'] for k,v in r['per_kernel'].items()})
-    print(r.get('sweep_error'))
-except Exception as e: print('parse failed',e)
+def load(f): return [d for d in map(json.loads,open(f)) if d.get('op')=='attn2']
+a,b=load('gpurun_out/r2/mb_nopf.jsonl'),load('gpurun_out/r2/mb_pf.jsonl')
+for x,y in zip(a,b): print(x['N'],x['C'],x['L'],'fwd nopf %.1f pf %.1f | bwd nopf %.1f pf %.1f | fb %.3f -> %.3f'%(x['fwd_us'],y['fwd_us'],x['bwd_us'],y['bwd_us'],x['fwdbwd_frac'],y['fwdbwd_frac']))
 PY
+for lib in nopf product; do for m in fwd bwd; do for cfg in "1024 1280" "4096 640"; do set -- $cfg
+  if [ $lib = nopf ]; then export PEA_B200_LIB=$T/libpea_nopf.so; else unset PEA_B200_LIB; fi
+  timeout 100 python tools/chain_probe.py --mode $m --N $1 --C $2 2>/dev/null | python -c "
+import sys,json
+d=json.loads(sys.stdin.read()); print('$lib',d['mode'],d['N'],d['C'],'marginal %.2f bracketed %.2f'%(d['marginal_us_per_launch'],d['bracketed_us_median']))"
+done; done; done
