@@ -508,13 +508,15 @@ def adapter_subrun(dev, replays=20):
     torch.manual_seed(0)
     x = torch.randn(16, 77, 1024, device=dev)
     res = {}
-    for name in ("library", "pytorch_bf16_autocast"):
-        m = (A.MLP(1024, 1280, 1024, 2048, False, precision="bf16") if name == "library" else TorchMLP()).to(dev)
+    pdl_default = A.PDL_CHAIN
+    for name in ("library", "library_plain_launches", "pytorch_bf16_autocast"):
+        A.PDL_CHAIN = pdl_default and name == "library"     # second arm: the same chain without PEA_LAUNCH_PDL
+        m = (A.MLP(1024, 1280, 1024, 2048, False, precision="bf16") if name.startswith("library") else TorchMLP()).to(dev)
 
         def fb():
             for p in m.parameters():
                 p.grad = None
-            if name == "library":
+            if name.startswith("library"):
                 x1, x2 = m(x)
             else:
                 with torch.autocast("cuda", dtype=torch.bfloat16):
@@ -533,6 +535,7 @@ def adapter_subrun(dev, replays=20):
             fb()
         res[name + "_us"] = time_replays(g, replays) * 1e3
         del g
+    A.PDL_CHAIN = pdl_default
     res["flops_fwd_bwd"] = 6 * 1232 * 6029312
     res["library_TFLOPs"] = res["flops_fwd_bwd"] / res["library_us"] / 1e6
     res["how"] = "CUDA-graph replay of one forward+backward (loss = sum(x1) + mean(x2^2)), median of %d, rows M = 1232" % replays

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define PEA_B200_VERSION 200 /* 0.2.0: flags on the gemm / attn2 descriptors, inv_prescale on pea_kd_scale_grads */
+#define PEA_B200_VERSION 201 /* 0.2.1: flags on the row helpers; 0.2.0: flags on the gemm / attn2 descriptors, inv_prescale on pea_kd_scale_grads */
 
 enum { PEA_OK = 0, PEA_EINVAL = -1, PEA_ECUDA = -2, PEA_ENODEV = -3, PEA_EUNSUPPORTED = -4 };
 /* `flags` of pea_gemm_desc / pea_attn2_desc.
@@ -146,23 +146,33 @@ int pea_gemm(const pea_gemm_desc* desc, void* stream);
 
 /* ----------------------------------------------------------------------------------------------------------
  * Row-wise helpers of the adapter (LayerNorm of train_sdxl_zh.py:47,60; torch.mean(x, 1) of :66; the
- * bias gradient; operand splitting) and the CFG-dropout select of train_sdxl_zh.py:392-395.
+ * bias gradient; operand splitting) and the CFG-dropout select of train_sdxl_zh.py:392-395.  `flags`: PEA_LAUNCH_*
+ * (the adapter chains its launches with PEA_LAUNCH_PDL; every kernel orders its accesses with griddepcontrol.wait).
  * -------------------------------------------------------------------------------------------------------- */
 int pea_layernorm_fwd(const void* d_x, pea_dtype x_dtype, const float* d_gamma, const float* d_beta, int M, int D,
                       float eps, void* const d_y_planes[3], int nsplit, pea_dtype plane_dtype, float* d_mean,
-                      float* d_rstd, void* stream);
+                      float* d_rstd, unsigned flags, void* stream);
 /* dgamma/dbeta are ACCUMULATED (+=) so two calls (cond + uncond) can share them; dx optional. */
 int pea_layernorm_bwd(const void* d_x, pea_dtype x_dtype, const float* d_dy, const float* d_gamma,
                       const float* d_mean, const float* d_rstd, int M, int D, float* d_dgamma, float* d_dbeta,
-                      float* d_dx, void* stream);
+                      float* d_dx, unsigned flags, void* stream);
 /* planes = split_S(x): x fp32/bf16/fp16 [rows, cols] with row stride ld -> S dense planes of plane_dtype. */
 int pea_split_planes(const void* d_x, pea_dtype x_dtype, long long rows, long long cols, long long ld,
-                     void* const d_planes[3], int nsplit, pea_dtype plane_dtype, void* stream);
+                     void* const d_planes[3], int nsplit, pea_dtype plane_dtype, unsigned flags, void* stream);
+/* The same for `count` tensors of one dtype in ONE launch when each is dense fp32 with 8 | rows*cols (the adapter's weight
+ * matrices, re-split every step: train_sdxl_zh.py:58-67 under fp16/bf16 autocast); otherwise one launch per tensor. */
+typedef struct pea_split_item {
+  const void* d_x; long long rows, cols, ld;
+  void* d_planes[3];
+} pea_split_item;
+int pea_split_planes_multi(const pea_split_item* items, int count, pea_dtype x_dtype, int nsplit, pea_dtype plane_dtype,
+                           unsigned flags, void* stream);
 /* out[b, n] = mean_l (x[b*L + l, n] (+ res[b*L + l, n])), fp32 in/out (x1 of train_sdxl_zh.py:64-66). */
 int pea_mean_tokens(const float* d_x, const void* d_res, pea_dtype res_dtype, int B, int L, int D, float* d_out,
-                    void* stream);
+                    unsigned flags, void* stream);
 /* out[n] += sum_m x[m, n]  (bias gradient). */
-int pea_colsum_accum(const void* d_x, pea_dtype x_dtype, int M, int N, long long ld, float* d_out, void* stream);
+int pea_colsum_accum(const void* d_x, pea_dtype x_dtype, int M, int N, long long ld, float* d_out, unsigned flags,
+                     void* stream);
 /* out[b] = mask[b] ? a[b] : c[b] over rows of `row_elems` elements (CFG dropout), and its backward routing. */
 int pea_cfg_select(const unsigned char* d_mask, const void* d_uncond, const void* d_cond, void* d_out, int B,
                    long long row_elems, pea_dtype dtype, void* stream);

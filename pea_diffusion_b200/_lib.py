@@ -41,6 +41,10 @@ class KdTap(C.Structure):
     ]
 
 
+class SplitItem(C.Structure):
+    _fields_ = [("d_x", C.c_void_p), ("rows", C.c_longlong), ("cols", C.c_longlong), ("ld", C.c_longlong), ("d_planes", C.c_void_p * 3)]
+
+
 class Attn2Desc(C.Structure):
     _fields_ = [
         ("B", C.c_int), ("N", C.c_int), ("L", C.c_int), ("H", C.c_int), ("d", C.c_int),
@@ -87,13 +91,14 @@ SYMBOLS = {
     "pea_attn2_bwd": (C.c_int, [C.POINTER(Attn2Desc), C.c_void_p]),
     "pea_gemm": (C.c_int, [C.POINTER(GemmDesc), C.c_void_p]),
     "pea_layernorm_fwd": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float,
-                                    C.POINTER(_VP3), C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+                                    C.POINTER(_VP3), C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_uint, C.c_void_p]),
     "pea_layernorm_bwd": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
-                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint, C.c_void_p]),
     "pea_split_planes": (C.c_int, [C.c_void_p, C.c_int, C.c_longlong, C.c_longlong, C.c_longlong, C.POINTER(_VP3), C.c_int,
-                                   C.c_int, C.c_void_p]),
-    "pea_mean_tokens": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
-    "pea_colsum_accum": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_void_p, C.c_void_p]),
+                                   C.c_int, C.c_uint, C.c_void_p]),
+    "pea_split_planes_multi": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint, C.c_void_p]),
+    "pea_mean_tokens": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_uint, C.c_void_p]),
+    "pea_colsum_accum": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_void_p, C.c_uint, C.c_void_p]),
     "pea_add_noise": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
                                 C.c_int, C.c_longlong, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "pea_cfg_select": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_int, C.c_void_p]),

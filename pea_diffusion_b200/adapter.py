@@ -18,6 +18,7 @@ Precision modes (``precision=``):
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional, Sequence, Tuple
 
 import torch
@@ -26,6 +27,10 @@ import torch.nn as nn
 from . import ops
 
 Tensor = torch.Tensor
+
+# Every launch of the adapter's forward / backward chain carries PEA_LAUNCH_PDL (include/pea_b200.h): the chain is ~30
+# launches of a few microseconds each, so the launch-to-launch gap is a third of its time.  PEA_ADAPTER_PDL=0 disables (A/B).
+PDL_CHAIN = os.environ.get("PEA_ADAPTER_PDL", "1") != "0"
 
 
 def _mode(precision: Optional[str], param_dtype: torch.dtype) -> Tuple[int, torch.dtype]:
@@ -62,11 +67,11 @@ class _AdapterFn(torch.autograd.Function):
             x2d = x2d.contiguous()
         Ws = [wb[2 * i] for i in range(n_chain + int(head))]
         bs = [wb[2 * i + 1] for i in range(n_chain + int(head))]
-        w_planes = [ops.split_planes(w.detach(), nsplit, plane_dt) for w in Ws]
+        w_planes = ops.split_planes_multi([w.detach() for w in Ws], nsplit, plane_dt, pdl=PDL_CHAIN)   # one launch
         b_f32 = [None if b is None else b.detach().to(f32).contiguous() for b in bs]
 
         h, mean, rstd = ops.layernorm_fwd(x2d, ln_w.detach().to(f32).contiguous(), ln_b.detach().to(f32).contiguous(), 1e-5,
-                                          nsplit, plane_dt)
+                                          nsplit, plane_dt, pdl=PDL_CHAIN)
         inputs: List[List[Tensor]] = []   # A operand (planes) of every GEMM, kept for dW
         preacts: List[Tensor] = []        # fp32 pre-activation of every chain layer, kept for GELU'
         for i in range(n_chain):
@@ -77,19 +82,19 @@ class _AdapterFn(torch.autograd.Function):
             nxt = None
             if not last or head:
                 nxt = [torch.empty(M, N, device=dev, dtype=plane_dt) for _ in range(nsplit)]
-            ops.gemm(h, w_planes[i], M, N, Ws[i].shape[1], bias=b_f32[i], out0=a, out1=nxt, act=True)
+            ops.gemm(h, w_planes[i], M, N, Ws[i].shape[1], bias=b_f32[i], out0=a, out1=nxt, act=True, pdl=PDL_CHAIN)
             preacts.append(a)
             h = nxt
         xlast = preacts[-1]
         outs = []
         if pooled:
-            x1 = ops.mean_tokens(xlast, B, L, res=x2d if residual else None)
+            x1 = ops.mean_tokens(xlast, B, L, res=x2d if residual else None, pdl=PDL_CHAIN)
             outs.append(x1.to(x.dtype))
         if head:
             inputs.append(h)
             N = Ws[n_chain].shape[0]
             x2 = torch.empty(M, N, device=dev, dtype=x.dtype)
-            ops.gemm(h, w_planes[n_chain], M, N, Ws[n_chain].shape[1], bias=b_f32[n_chain], out0=x2)
+            ops.gemm(h, w_planes[n_chain], M, N, Ws[n_chain].shape[1], bias=b_f32[n_chain], out0=x2, pdl=PDL_CHAIN)
             outs.append(x2.view(B, L, N))
         else:
             outs.append(xlast.to(x.dtype).view(B, L, -1))
@@ -115,49 +120,69 @@ class _AdapterFn(torch.autograd.Function):
         dbs: List[Optional[Tensor]] = [None] * n_lin
         rowadd = None if g_pool is None else g_pool.detach().to(f32).contiguous()
 
+        # fp32 accumulators of the reduction kernels (bias gradients, dgamma, dbeta).  With a sink whose slot is fp32 the
+        # kernels accumulate straight into the (zeroed) slot; everything else is carved from ONE zero-filled buffer.
+        Dln = x2d.shape[1]
+        need = 2 * Dln + sum(Ws[i].shape[0] for i in range(n_lin) if bs[i] is not None and bs[i].requires_grad)
+        zpool, zoff = torch.zeros(need, device=dev, dtype=f32), [0]
+
+        def accumulator(prm: Tensor, n: int) -> Tuple[Tensor, Optional[Tensor]]:
+            """-> (fp32 accumulator of n zeros, the sink slot of `prm` or None)"""
+            slot = sink.slot(prm) if sink is not None else None
+            if slot is not None and slot.dtype == f32 and slot.is_contiguous():
+                return slot.view(-1).zero_(), slot
+            z = zpool[zoff[0]:zoff[0] + n]
+            zoff[0] += n
+            return z, slot
+
+        def deliver(prm: Tensor, acc: Tensor, slot: Optional[Tensor]) -> Optional[Tensor]:
+            """-> the gradient to hand to autograd (None when it went to the sink)"""
+            if slot is None:
+                return acc.to(prm.dtype).view_as(prm)
+            if slot.data_ptr() != acc.data_ptr():
+                slot.copy_(acc.view_as(slot))
+            sink.mark_ready(prm)
+            return None
+
         def weight_grads(i: int, g_planes: Sequence[Tensor], g_full: Optional[Tensor]):
             W = Ws[i]
             if W.requires_grad:
                 slot = sink.slot(W) if sink is not None else None
                 dW = slot if slot is not None else torch.empty(W.shape, device=dev, dtype=W.dtype)
                 # dW[o, k] = sum_r g[r, o] h[r, k]: both operands are stored [rows, *] -> MN-major
-                ops.gemm(g_planes, inputs[i], W.shape[0], W.shape[1], M, a_kmajor=False, b_kmajor=False, out0=dW)
+                ops.gemm(g_planes, inputs[i], W.shape[0], W.shape[1], M, a_kmajor=False, b_kmajor=False, out0=dW,
+                         pdl=PDL_CHAIN)
                 if slot is None:
                     dWs[i] = dW
                 else:
                     sink.mark_ready(W)
             if bs[i] is not None and bs[i].requires_grad:
-                db = torch.zeros(W.shape[0], device=dev, dtype=f32)
-                ops.colsum_accum(g_full if g_full is not None else g_planes[0], db)
+                db, slot = accumulator(bs[i], W.shape[0])
+                ops.colsum_accum(g_full if g_full is not None else g_planes[0], db, pdl=PDL_CHAIN)
                 if g_full is None:
                     for extra in g_planes[1:]:
-                        ops.colsum_accum(extra, db)
-                slot = sink.slot(bs[i]) if sink is not None else None
-                if slot is None:
-                    dbs[i] = db.to(bs[i].dtype)
-                else:
-                    slot.copy_(db)
-                    sink.mark_ready(bs[i])
+                        ops.colsum_accum(extra, db, pdl=PDL_CHAIN)
+                dbs[i] = deliver(bs[i], db, slot)
 
         # ---- gradient w.r.t. the last chain pre-activation x -------------------------------------------------
         if head:
             if g_main is None:
                 g_main = torch.zeros(M, Ws[n_chain].shape[0], device=dev, dtype=x2d.dtype)
             g2d = g_main.detach().reshape(M, -1)
-            g_planes = ops.split_planes(g2d, nsplit, plane_dt)
+            g_planes = ops.split_planes(g2d, nsplit, plane_dt, pdl=PDL_CHAIN)
             weight_grads(n_chain, g_planes, g2d)
             N = Ws[n_chain].shape[1]
             nxt = [torch.empty(M, N, device=dev, dtype=plane_dt) for _ in range(nsplit)]
             full = torch.empty(M, N, device=dev, dtype=f32) if bs[n_chain - 1] is not None else None
             # dx = (g2 @ Wfc) * GELU'(x) + dx1[b] / L
             ops.gemm(g_planes, w_planes[n_chain], M, N, Ws[n_chain].shape[0], b_kmajor=False, aux=preacts[-1], rowadd=rowadd,
-                     rowadd_group=L, rowadd_scale=1.0 / L, out0=full, out1=nxt)
+                     rowadd_group=L, rowadd_scale=1.0 / L, out0=full, out1=nxt, pdl=PDL_CHAIN)
             g_planes, g_full = nxt, full
         else:
             g = g_main.detach().reshape(M, -1).to(f32)
             if rowadd is not None:
                 g = g + (rowadd / L).repeat_interleave(L, dim=0)
-            g_planes, g_full = ops.split_planes(g.contiguous(), nsplit, plane_dt), g
+            g_planes, g_full = ops.split_planes(g.contiguous(), nsplit, plane_dt, pdl=PDL_CHAIN), g
 
         # ---- chain, last to first -------------------------------------------------------------------------------
         dh0 = None
@@ -167,17 +192,17 @@ class _AdapterFn(torch.autograd.Function):
             if i > 0:
                 nxt = [torch.empty(M, N, device=dev, dtype=plane_dt) for _ in range(nsplit)]
                 full = torch.empty(M, N, device=dev, dtype=f32) if bs[i - 1] is not None else None
-                ops.gemm(g_planes, w_planes[i], M, N, Ws[i].shape[0], b_kmajor=False, aux=preacts[i - 1], out0=full, out1=nxt)
+                ops.gemm(g_planes, w_planes[i], M, N, Ws[i].shape[0], b_kmajor=False, aux=preacts[i - 1], out0=full, out1=nxt,
+                         pdl=PDL_CHAIN)
                 g_planes, g_full = nxt, full
             else:
                 dh0 = torch.empty(M, N, device=dev, dtype=f32)
-                ops.gemm(g_planes, w_planes[0], M, N, Ws[0].shape[0], b_kmajor=False, out0=dh0)
+                ops.gemm(g_planes, w_planes[0], M, N, Ws[0].shape[0], b_kmajor=False, out0=dh0, pdl=PDL_CHAIN)
 
         # ---- LayerNorm ------------------------------------------------------------------------------------------
         want_dx = ctx.needs_input_grad[6]
-        dgamma = torch.zeros(x2d.shape[1], device=dev, dtype=f32)
-        dbeta = torch.zeros(x2d.shape[1], device=dev, dtype=f32)
-        dx = ops.layernorm_bwd(x2d, dh0, ln_w.detach().to(f32).contiguous(), mean, rstd, dgamma, dbeta, want_dx)
+        (dgamma, slot_g), (dbeta, slot_b) = accumulator(ln_w, Dln), accumulator(ln_b, Dln)
+        dx = ops.layernorm_bwd(x2d, dh0, ln_w.detach().to(f32).contiguous(), mean, rstd, dgamma, dbeta, want_dx, pdl=PDL_CHAIN)
         if want_dx:
             if residual and rowadd is not None:
                 dx = dx + (rowadd / L).repeat_interleave(L, dim=0)
@@ -185,15 +210,7 @@ class _AdapterFn(torch.autograd.Function):
         flat: List[Optional[Tensor]] = []
         for i in range(n_lin):
             flat += [dWs[i], dbs[i]]
-        g_lnw, g_lnb = dgamma.to(ln_w.dtype), dbeta.to(ln_w.dtype)
-        if sink is not None:
-            for prm, g in ((ln_w, g_lnw), (ln_b, g_lnb)):
-                slot = sink.slot(prm)
-                if slot is not None:
-                    slot.copy_(g)
-                    sink.mark_ready(prm)
-            g_lnw = None if sink.slot(ln_w) is not None else g_lnw
-            g_lnb = None if sink.slot(ln_b) is not None else g_lnb
+        g_lnw, g_lnb = deliver(ln_w, dgamma, slot_g), deliver(ln_b, dbeta, slot_b)
         return (None, None, None, None, None, None, dx if want_dx else None, g_lnw, g_lnb, None, *flat)
 
 

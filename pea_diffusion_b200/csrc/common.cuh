@@ -66,10 +66,10 @@ inline int ensure_dynamic_smem(Kernel kernel, int bytes, std::atomic<unsigned lo
 // Launch through cudaLaunchKernelEx; `pdl` adds cudaLaunchAttributeProgrammaticStreamSerialization (the kernel must then
 // order its global-memory accesses with pdl_wait(), below).
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_ex(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, bool pdl, Args&&... args) {
+inline cudaError_t launch_ex(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args&&... args) {
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3((unsigned)block);
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -79,6 +79,16 @@ inline cudaError_t launch_ex(void (*kernel)(KArgs...), int grid, int block, size
   cfg.numAttrs = pdl ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_ex(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, bool pdl, Args&&... args) {
+  return launch_ex(kernel, dim3((unsigned)grid), dim3((unsigned)block), smem, st, pdl, static_cast<Args&&>(args)...);
+}
+
+#define PEA_LAUNCH_EX(...)                 \
+  do {                                     \
+    PEA_CUDA(launch_ex(__VA_ARGS__));      \
+    PEA_LAUNCH_CHECK();                    \
+  } while (0)
 
 // ---- device helpers ------------------------------------------------------------------------------------------
 // Programmatic dependent launch.  pdl_wait(): block until the grid this one was launched behind has completed and its

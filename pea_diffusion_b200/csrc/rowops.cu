@@ -50,6 +50,8 @@ __device__ __forceinline__ void store_split(const Planes& pl, int nsplit, pea_dt
 __global__ void layernorm_fwd_kernel(const void* __restrict__ x, pea_dtype xdt, const float* __restrict__ gamma,
                                      const float* __restrict__ beta, int M, int D, float eps, Planes y, int nsplit,
                                      pea_dtype pdt, float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
@@ -73,6 +75,8 @@ template <int NV>
 __global__ void layernorm_fwd_vec_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                                          int M, float eps, Planes y, int nsplit, pea_dtype pdt, float* __restrict__ mean_out,
                                          float* __restrict__ rstd_out) {
+  pdl_wait();
+  pdl_launch_dependents();
   constexpr int D = NV * 128;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -108,6 +112,8 @@ __global__ void layernorm_fwd_vec_kernel(const float* __restrict__ x, const floa
 __global__ void layernorm_bwd_affine_kernel(const void* __restrict__ x, pea_dtype xdt, const float* __restrict__ dy,
                                             const float* __restrict__ mean, const float* __restrict__ rstd, int M, int D,
                                             float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  pdl_wait();
+  pdl_launch_dependents();
   __shared__ float sg[8][33], sb[8][33];
   const int col = blockIdx.x * 32 + threadIdx.x;
   const int rows_per = (M + gridDim.y - 1) / gridDim.y;
@@ -137,6 +143,8 @@ __global__ void layernorm_bwd_affine_kernel(const void* __restrict__ x, pea_dtyp
 __global__ void layernorm_bwd_dx_kernel(const void* __restrict__ x, pea_dtype xdt, const float* __restrict__ dy,
                                         const float* __restrict__ gamma, const float* __restrict__ mean,
                                         const float* __restrict__ rstd, int M, int D, float* __restrict__ dx) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
@@ -160,6 +168,8 @@ __global__ void layernorm_bwd_dx_kernel(const void* __restrict__ x, pea_dtype xd
 
 __global__ void split_planes_kernel(const void* __restrict__ x, pea_dtype xdt, long long rows, long long cols, long long ld,
                                     Planes pl, int nsplit, pea_dtype pdt) {
+  pdl_wait();
+  pdl_launch_dependents();
   const long long n = rows * cols;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / cols, c = i - r * cols;
@@ -169,7 +179,16 @@ __global__ void split_planes_kernel(const void* __restrict__ x, pea_dtype xdt, l
 
 // Contiguous fp32 source (ld == cols, 32-byte aligned, n % 8 == 0): 8 elements per thread per step, 128-bit loads, one
 // 128-bit store per plane, no index arithmetic beyond the grid stride.
-__global__ void split_planes_vec_kernel(const float* __restrict__ x, long long n8, Planes pl, int nsplit, pea_dtype pdt) {
+struct SplitItem { const float* x; long long n8; Planes pl; };
+constexpr int kSplitBatch = 8;
+struct SplitBatch { SplitItem it[kSplitBatch]; };     // blockIdx.y selects the tensor (pea_split_planes_multi: one launch)
+
+__global__ void split_planes_vec_kernel(const __grid_constant__ SplitBatch batch, int nsplit, pea_dtype pdt) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const float* __restrict__ x = batch.it[blockIdx.y].x;
+  const long long n8 = batch.it[blockIdx.y].n8;
+  const Planes pl = batch.it[blockIdx.y].pl;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
     const float4 a = reinterpret_cast<const float4*>(x)[2 * i], b = reinterpret_cast<const float4*>(x)[2 * i + 1];
     float r[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
@@ -200,6 +219,8 @@ __global__ void split_planes_vec_kernel(const float* __restrict__ x, long long n
 
 __global__ void mean_tokens_kernel(const float* __restrict__ x, const void* __restrict__ res, pea_dtype rdt, int L, int D,
                                    float* __restrict__ out) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   const int b = blockIdx.y;
   if (n >= D) return;
@@ -225,6 +246,8 @@ __global__ void mean_tokens_kernel(const float* __restrict__ x, const void* __re
 }
 
 __global__ void colsum_accum_kernel(const void* __restrict__ x, pea_dtype xdt, int M, int N, long long ld, float* __restrict__ out) {
+  pdl_wait();
+  pdl_launch_dependents();
   __shared__ float sm[8][33];
   const int col = blockIdx.x * 32 + threadIdx.x;
   const int rows_per = (M + gridDim.y - 1) / gridDim.y;
@@ -290,7 +313,7 @@ extern "C" int pea_add_noise(const void* d_latents, pea_dtype lat_dtype, const f
 
 extern "C" int pea_layernorm_fwd(const void* d_x, pea_dtype x_dtype, const float* d_gamma, const float* d_beta, int M, int D,
                                  float eps, void* const d_y_planes[3], int nsplit, pea_dtype plane_dtype, float* d_mean,
-                                 float* d_rstd, void* stream) {
+                                 float* d_rstd, unsigned flags, void* stream) {
   PEA_CHECK_ARG(d_x && d_gamma && d_beta && d_y_planes && d_mean && d_rstd, "layernorm_fwd: null pointer");
   PEA_CHECK_ARG(M >= 1 && D >= 1 && nsplit >= 1 && nsplit <= 3, "layernorm_fwd: bad M/D/nsplit");
   PEA_CHECK_ARG(plane_dtype != PEA_F32, "layernorm_fwd: planes are 16-bit");
@@ -300,19 +323,21 @@ extern "C" int pea_layernorm_fwd(const void* d_x, pea_dtype x_dtype, const float
   const bool vec = x_dtype == PEA_F32 && D % 128 == 0 && D <= 2048 && al16(d_x) && al16(d_gamma) && al16(d_beta);
   cudaStream_t st = (cudaStream_t)stream;
   const float* xf = static_cast<const float*>(d_x);
-#define PEA_LN_VEC(NV) layernorm_fwd_vec_kernel<NV><<<(M + 3) / 4, 128, 0, st>>>(xf, d_gamma, d_beta, M, eps, pl, nsplit, plane_dtype, d_mean, d_rstd)
+  const bool pdl = (flags & PEA_LAUNCH_PDL) != 0;
+#define PEA_LN_VEC(NV) PEA_LAUNCH_EX(layernorm_fwd_vec_kernel<NV>, (M + 3) / 4, 128, 0, st, pdl, xf, d_gamma, d_beta, M, eps, pl, nsplit, plane_dtype, d_mean, d_rstd)
   if (vec && D == 1024) PEA_LN_VEC(8);
   else if (vec && D == 768) PEA_LN_VEC(6);
   else if (vec && D == 2048) PEA_LN_VEC(16);
   else if (vec && D == 128) PEA_LN_VEC(1);
-  else layernorm_fwd_kernel<<<(M + 3) / 4, 128, 0, st>>>(d_x, x_dtype, d_gamma, d_beta, M, D, eps, pl, nsplit, plane_dtype, d_mean, d_rstd);
+  else PEA_LAUNCH_EX(layernorm_fwd_kernel, (M + 3) / 4, 128, 0, st, pdl, d_x, x_dtype, d_gamma, d_beta, M, D, eps, pl, nsplit, plane_dtype, d_mean, d_rstd);
 #undef PEA_LN_VEC
   PEA_LAUNCH_CHECK();
   return PEA_OK;
 }
 
 extern "C" int pea_layernorm_bwd(const void* d_x, pea_dtype x_dtype, const float* d_dy, const float* d_gamma, const float* d_mean,
-                                 const float* d_rstd, int M, int D, float* d_dgamma, float* d_dbeta, float* d_dx, void* stream) {
+                                 const float* d_rstd, int M, int D, float* d_dgamma, float* d_dbeta, float* d_dx, unsigned flags,
+                                 void* stream) {
   PEA_CHECK_ARG(d_x && d_dy && d_gamma && d_mean && d_rstd && d_dgamma && d_dbeta, "layernorm_bwd: null pointer");
   PEA_CHECK_ARG(M >= 1 && D >= 1, "layernorm_bwd: bad M/D");
   // enough row chunks to cover the machine (D = 1024: 32 column blocks x 8 row chunks); at least 64 rows per chunk
@@ -320,54 +345,93 @@ extern "C" int pea_layernorm_bwd(const void* d_x, pea_dtype x_dtype, const float
   int rc = (2 * num_sms() + cb - 1) / cb;
   if (rc > (M + 63) / 64) rc = (M + 63) / 64;
   if (rc < 1) rc = 1;
-  layernorm_bwd_affine_kernel<<<dim3(cb, rc), dim3(32, 8), 0, (cudaStream_t)stream>>>(d_x, x_dtype, d_dy, d_mean, d_rstd, M, D,
-                                                                                   d_dgamma, d_dbeta);
-  PEA_LAUNCH_CHECK();
-  if (d_dx) {
-    layernorm_bwd_dx_kernel<<<(M + 3) / 4, 128, 0, (cudaStream_t)stream>>>(d_x, x_dtype, d_dy, d_gamma, d_mean, d_rstd, M, D, d_dx);
-    PEA_LAUNCH_CHECK();
-  }
+  const bool pdl = (flags & PEA_LAUNCH_PDL) != 0;
+  PEA_LAUNCH_EX(layernorm_bwd_affine_kernel, dim3(cb, rc), dim3(32, 8), 0, (cudaStream_t)stream, pdl, d_x, x_dtype, d_dy, d_mean,
+                        d_rstd, M, D, d_dgamma, d_dbeta);
+  if (d_dx)
+    PEA_LAUNCH_EX(layernorm_bwd_dx_kernel, (M + 3) / 4, 128, 0, (cudaStream_t)stream, pdl, d_x, x_dtype, d_dy, d_gamma, d_mean,
+                          d_rstd, M, D, d_dx);
   return PEA_OK;
 }
 
 extern "C" int pea_split_planes(const void* d_x, pea_dtype x_dtype, long long rows, long long cols, long long ld,
-                                void* const d_planes[3], int nsplit, pea_dtype plane_dtype, void* stream) {
+                                void* const d_planes[3], int nsplit, pea_dtype plane_dtype, unsigned flags, void* stream) {
   PEA_CHECK_ARG(d_x && d_planes && rows >= 1 && cols >= 1 && ld >= cols, "split_planes: bad arguments");
   PEA_CHECK_ARG(nsplit >= 1 && nsplit <= 3 && plane_dtype != PEA_F32, "split_planes: bad nsplit/plane dtype");
   Planes pl{};
   for (int s = 0; s < nsplit; ++s) { PEA_CHECK_ARG(d_planes[s], "split_planes: null plane %d", s); pl.p[s] = d_planes[s]; }
   const long long n = rows * cols;
+  const bool pdl = (flags & PEA_LAUNCH_PDL) != 0;
   bool vec = x_dtype == PEA_F32 && ld == cols && n % 8 == 0 && (reinterpret_cast<uintptr_t>(d_x) & 31) == 0;
   for (int s = 0; s < nsplit; ++s) vec = vec && (reinterpret_cast<uintptr_t>(d_planes[s]) & 15) == 0;
   if (vec) {
     const long long n8 = n / 8;
     const int grid = (int)((n8 + 255) / 256 < (long long)num_sms() * 16 ? (n8 + 255) / 256 : (long long)num_sms() * 16);
-    split_planes_vec_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(static_cast<const float*>(d_x), n8, pl, nsplit, plane_dtype);
-    PEA_LAUNCH_CHECK();
+    SplitBatch batch{};
+    batch.it[0] = SplitItem{static_cast<const float*>(d_x), n8, pl};
+    PEA_LAUNCH_EX(split_planes_vec_kernel, grid, 256, 0, (cudaStream_t)stream, pdl, batch, nsplit, plane_dtype);
     return PEA_OK;
   }
   const int grid = (int)((n + 255) / 256 < (long long)num_sms() * 16 ? (n + 255) / 256 : (long long)num_sms() * 16);
-  split_planes_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_x, x_dtype, rows, cols, ld, pl, nsplit, plane_dtype);
-  PEA_LAUNCH_CHECK();
+  PEA_LAUNCH_EX(split_planes_kernel, grid, 256, 0, (cudaStream_t)stream, pdl, d_x, x_dtype, rows, cols, ld, pl, nsplit, plane_dtype);
+  return PEA_OK;
+}
+
+extern "C" int pea_split_planes_multi(const pea_split_item* items, int count, pea_dtype x_dtype, int nsplit, pea_dtype plane_dtype,
+                                      unsigned flags, void* stream) {
+  PEA_CHECK_ARG(items && count >= 1, "split_planes_multi: bad arguments");
+  PEA_CHECK_ARG(nsplit >= 1 && nsplit <= 3 && plane_dtype != PEA_F32, "split_planes_multi: bad nsplit/plane dtype");
+  // one launch when every tensor takes the vector path (dense fp32, 8 | n, aligned) -- the adapter's weights; else one call each
+  bool vec = x_dtype == PEA_F32 && count <= kSplitBatch;
+  long long n8_max = 0;
+  SplitBatch batch{};
+  for (int i = 0; i < count && vec; ++i) {
+    const pea_split_item& it = items[i];
+    PEA_CHECK_ARG(it.d_x && it.rows >= 1 && it.cols >= 1 && it.ld >= it.cols, "split_planes_multi: bad item %d", i);
+    const long long n = it.rows * it.cols;
+    vec = it.ld == it.cols && n % 8 == 0 && (reinterpret_cast<uintptr_t>(it.d_x) & 31) == 0;
+    for (int s = 0; s < nsplit; ++s) {
+      PEA_CHECK_ARG(it.d_planes[s], "split_planes_multi: item %d: null plane %d", i, s);
+      vec = vec && (reinterpret_cast<uintptr_t>(it.d_planes[s]) & 15) == 0;
+      batch.it[i].pl.p[s] = it.d_planes[s];
+    }
+    batch.it[i].x = static_cast<const float*>(it.d_x);
+    batch.it[i].n8 = n / 8;
+    if (n / 8 > n8_max) n8_max = n / 8;
+  }
+  if (!vec) {
+    for (int i = 0; i < count; ++i) {
+      const int rc = pea_split_planes(items[i].d_x, x_dtype, items[i].rows, items[i].cols, items[i].ld, items[i].d_planes, nsplit,
+                                      plane_dtype, flags, stream);
+      if (rc != PEA_OK) return rc;
+    }
+    return PEA_OK;
+  }
+  long long gx = (n8_max + 255) / 256;
+  const long long cap = ((long long)num_sms() * 16 + count - 1) / count;
+  if (gx > cap) gx = cap;
+  PEA_LAUNCH_EX(split_planes_vec_kernel, dim3((unsigned)gx, (unsigned)count), dim3(256), 0, (cudaStream_t)stream,
+                     (flags & PEA_LAUNCH_PDL) != 0, batch, nsplit, plane_dtype);
   return PEA_OK;
 }
 
 extern "C" int pea_mean_tokens(const float* d_x, const void* d_res, pea_dtype res_dtype, int B, int L, int D, float* d_out,
-                               void* stream) {
+                               unsigned flags, void* stream) {
   PEA_CHECK_ARG(d_x && d_out && B >= 1 && L >= 1 && D >= 1, "mean_tokens: bad arguments");
-  mean_tokens_kernel<<<dim3((D + 127) / 128, B), 128, 0, (cudaStream_t)stream>>>(d_x, d_res, res_dtype, L, D, d_out);
-  PEA_LAUNCH_CHECK();
+  PEA_LAUNCH_EX(mean_tokens_kernel, dim3((D + 127) / 128, B), dim3(128), 0, (cudaStream_t)stream, (flags & PEA_LAUNCH_PDL) != 0,
+                        d_x, d_res, res_dtype, L, D, d_out);
   return PEA_OK;
 }
 
-extern "C" int pea_colsum_accum(const void* d_x, pea_dtype x_dtype, int M, int N, long long ld, float* d_out, void* stream) {
+extern "C" int pea_colsum_accum(const void* d_x, pea_dtype x_dtype, int M, int N, long long ld, float* d_out, unsigned flags,
+                                void* stream) {
   PEA_CHECK_ARG(d_x && d_out && M >= 1 && N >= 1 && ld >= N, "colsum_accum: bad arguments");
   const int cb = (N + 31) / 32;
   int rc = (2 * num_sms() + cb - 1) / cb;
   if (rc > (M + 63) / 64) rc = (M + 63) / 64;
   if (rc < 1) rc = 1;
-  colsum_accum_kernel<<<dim3(cb, rc), dim3(32, 8), 0, (cudaStream_t)stream>>>(d_x, x_dtype, M, N, ld, d_out);
-  PEA_LAUNCH_CHECK();
+  PEA_LAUNCH_EX(colsum_accum_kernel, dim3(cb, rc), dim3(32, 8), 0, (cudaStream_t)stream, (flags & PEA_LAUNCH_PDL) != 0, d_x, x_dtype,
+                        M, N, ld, d_out);
   return PEA_OK;
 }
 

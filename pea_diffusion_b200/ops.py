@@ -126,7 +126,11 @@ def gemm(A: Sequence[Tensor], B: Sequence[Tensor], M: int, N: int, K: int, *, a_
         check(lib.pea_gemm(C.byref(d), stream_ptr(A[0].device)), "pea_gemm")
 
 
-def split_planes(x: Tensor, nsplit: int, plane_dtype: torch.dtype) -> Planes:
+def _flags(pdl: bool) -> int:
+    return _lib.PEA_LAUNCH_PDL if pdl else 0
+
+
+def split_planes(x: Tensor, nsplit: int, plane_dtype: torch.dtype, pdl: bool = False) -> Planes:
     """x [rows, cols] (any float dtype, unit column stride) -> ``nsplit`` dense 16-bit planes summing to x."""
     require_cuda(x)
     _row_major_2d(x)
@@ -135,11 +139,41 @@ def split_planes(x: Tensor, nsplit: int, plane_dtype: torch.dtype) -> Planes:
         return [x]  # already a valid single plane: no copy
     planes = [torch.empty(rows, cols, device=x.device, dtype=plane_dtype) for _ in range(nsplit)]
     check(lib.pea_split_planes(x.data_ptr(), dtype_code(x.dtype), rows, cols, x.stride(0), C.byref(planes3(planes)), nsplit,
-                               dtype_code(plane_dtype), stream_ptr(x.device)), "pea_split_planes")
+                               dtype_code(plane_dtype), _flags(pdl), stream_ptr(x.device)), "pea_split_planes")
     return planes
 
 
-def layernorm_fwd(x: Tensor, gamma: Tensor, beta: Tensor, eps: float, nsplit: int, plane_dtype: torch.dtype):
+def split_planes_multi(xs: Sequence[Tensor], nsplit: int, plane_dtype: torch.dtype, pdl: bool = False) -> List[Planes]:
+    """split_planes of several tensors of one dtype -- ONE launch when all are dense fp32 (the adapter's weights, re-split
+    every step)."""
+    require_cuda(*xs)
+    out: List[Optional[Planes]] = [None] * len(xs)
+    todo = []
+    for i, x in enumerate(xs):
+        _row_major_2d(x)
+        if nsplit == 1 and x.dtype == plane_dtype and x.stride(0) % 8 == 0 and x.data_ptr() % 16 == 0:
+            out[i] = [x]
+        else:
+            todo.append(i)
+    by_dtype = {}
+    for i in todo:
+        by_dtype.setdefault(xs[i].dtype, []).append(i)
+    for dt, idx in by_dtype.items():
+        for k in range(0, len(idx), 8):
+            chunk = idx[k:k + 8]
+            items = (_lib.SplitItem * len(chunk))()
+            for it, i in zip(items, chunk):
+                x = xs[i]
+                out[i] = [torch.empty(x.shape[0], x.shape[1], device=x.device, dtype=plane_dtype) for _ in range(nsplit)]
+                it.d_x, it.rows, it.cols, it.ld = x.data_ptr(), x.shape[0], x.shape[1], x.stride(0)
+                for s, pl in enumerate(out[i]):
+                    it.d_planes[s] = pl.data_ptr()
+            check(lib.pea_split_planes_multi(C.cast(items, C.c_void_p), len(chunk), dtype_code(dt), nsplit, dtype_code(plane_dtype),
+                                             _flags(pdl), stream_ptr(xs[chunk[0]].device)), "pea_split_planes_multi")
+    return out
+
+
+def layernorm_fwd(x: Tensor, gamma: Tensor, beta: Tensor, eps: float, nsplit: int, plane_dtype: torch.dtype, pdl: bool = False):
     """x [M, D] contiguous -> (planes of LN(x), mean [M], rstd [M]); statistics in fp32."""
     require_cuda(x, gamma, beta)
     M, D = x.shape
@@ -148,38 +182,39 @@ def layernorm_fwd(x: Tensor, gamma: Tensor, beta: Tensor, eps: float, nsplit: in
     rstd = torch.empty(M, device=x.device, dtype=torch.float32)
     check(lib.pea_layernorm_fwd(x.data_ptr(), dtype_code(x.dtype), gamma.data_ptr(), beta.data_ptr(), M, D, eps,
                                 C.byref(planes3(planes)), nsplit, dtype_code(plane_dtype), mean.data_ptr(), rstd.data_ptr(),
-                                stream_ptr(x.device)), "pea_layernorm_fwd")
+                                _flags(pdl), stream_ptr(x.device)), "pea_layernorm_fwd")
     return planes, mean, rstd
 
 
 def layernorm_bwd(x: Tensor, dy: Tensor, gamma: Tensor, mean: Tensor, rstd: Tensor, dgamma: Tensor, dbeta: Tensor,
-                  want_dx: bool) -> Optional[Tensor]:
+                  want_dx: bool, pdl: bool = False) -> Optional[Tensor]:
     """dgamma/dbeta (fp32) are accumulated into; returns dx (fp32) when asked."""
     require_cuda(x, dy)
     M, D = x.shape
     dx = torch.empty(M, D, device=x.device, dtype=torch.float32) if want_dx else None
     check(lib.pea_layernorm_bwd(x.data_ptr(), dtype_code(x.dtype), dy.data_ptr(), gamma.data_ptr(), mean.data_ptr(),
-                                rstd.data_ptr(), M, D, dgamma.data_ptr(), dbeta.data_ptr(), ptr(dx), stream_ptr(x.device)),
+                                rstd.data_ptr(), M, D, dgamma.data_ptr(), dbeta.data_ptr(), ptr(dx), _flags(pdl),
+                                stream_ptr(x.device)),
           "pea_layernorm_bwd")
     return dx
 
 
-def mean_tokens(x: Tensor, B: int, L: int, res: Optional[Tensor] = None) -> Tensor:
+def mean_tokens(x: Tensor, B: int, L: int, res: Optional[Tensor] = None, pdl: bool = False) -> Tensor:
     """x fp32 [B*L, D] (+ res [B*L, D]) -> [B, D] fp32 mean over the L tokens of each sample."""
     require_cuda(x, res)
     D = x.shape[-1]
     out = torch.empty(B, D, device=x.device, dtype=torch.float32)
     check(lib.pea_mean_tokens(x.data_ptr(), ptr(res), dtype_code(res.dtype) if res is not None else 0, B, L, D,
-                              out.data_ptr(), stream_ptr(x.device)), "pea_mean_tokens")
+                              out.data_ptr(), _flags(pdl), stream_ptr(x.device)), "pea_mean_tokens")
     return out
 
 
-def colsum_accum(x: Tensor, out: Tensor) -> None:
+def colsum_accum(x: Tensor, out: Tensor, pdl: bool = False) -> None:
     """out[n] += sum_m x[m, n]; out fp32."""
     require_cuda(x, out)
     _row_major_2d(x)
     check(lib.pea_colsum_accum(x.data_ptr(), dtype_code(x.dtype), x.shape[0], x.shape[1], x.stride(0), out.data_ptr(),
-                               stream_ptr(x.device)), "pea_colsum_accum")
+                               _flags(pdl), stream_ptr(x.device)), "pea_colsum_accum")
 
 
 def cfg_select(mask_u8: Tensor, uncond: Tensor, cond: Tensor) -> Tensor:

@@ -310,6 +310,55 @@ def test_adapter_full_size_fp32_and_bf16():
         m.load_state_dict({"bogus": torch.zeros(1)})
 
 
+def test_adapter_pdl_chain_matches_plain_launches():
+    """adapter.PDL_CHAIN only changes how the ~30 launches are chained (PEA_LAUNCH_PDL), never the results: same module,
+    same input, eagerly and inside a replayed CUDA graph (programmatic edges are captured and replayed)."""
+    from pea_diffusion_b200 import adapter as A
+    sd = O.adapter_init(1024, 1280, 1024, 2048, seed=0)
+    x = torch.randn(16, 77, 1024, generator=torch.Generator().manual_seed(7)).to(DEV)
+
+    def module():
+        m = A.MLP(1024, 1280, 1024, 2048, False)
+        m.load_state_dict(sd)
+        return m.to(DEV)
+
+    def fwd_bwd(m, xi):
+        for p in m.parameters():
+            p.grad = None
+        x1, x2 = m(xi)
+        (x1.square().sum() + x2.square().sum()).backward()
+        return x1, x2
+
+    res = {}
+    saved = A.PDL_CHAIN
+    try:
+        for pdl in (False, True):
+            A.PDL_CHAIN = pdl
+            m, xi = module(), x.clone().requires_grad_(True)
+            x1, x2 = fwd_bwd(m, xi)
+            res[pdl] = [x1.detach(), x2.detach(), xi.grad] + [p.grad for p in m.parameters()]
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            m, xg = module(), x.clone().requires_grad_(True)
+            for _ in range(2):
+                fwd_bwd(m, xg)
+                xg.grad = None
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                y1, y2 = fwd_bwd(m, xg)
+            for _ in range(3):
+                g.replay()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        res["graph"] = [y1.detach(), y2.detach(), xg.grad] + [p.grad for p in m.parameters()]
+    finally:
+        A.PDL_CHAIN = saved
+    for key in (True, "graph"):
+        for a, b in zip(res[False], res[key]):
+            assert rel_err(b, a) < 1e-5, key     # split-K atomics reorder fp32 sums, nothing else differs
+
+
 # ----------------------------------------------------------------------------------------------------------- KD loss
 @pytest.mark.parametrize("name,skip", [("loss_sdxl", False), ("loss_sd_nanskip", True)])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])

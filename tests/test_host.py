@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(dll, n), f"{n} declared in include/pea_b200.h but not exported"
     assert sorted(_lib.SYMBOLS) == names, "ctypes binding table and header disagree"
-    assert _lib.lib.pea_version() == 200
+    assert _lib.lib.pea_version() == 201
     nm = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
     assert "pea_gemm" in nm
 

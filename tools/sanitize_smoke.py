@@ -67,5 +67,12 @@ x = rn(154, 1024, dt=torch.float32)
 pl, mean, rstd = ops.layernorm_fwd(x, torch.ones(1024, device=dev), torch.zeros(1024, device=dev), 1e-5, 2, torch.bfloat16)
 ops.split_planes(rn(77, 1000, dt=torch.float32)[:, :996], 3, torch.bfloat16)
 ops.cfg_select(torch.tensor([1, 0], dtype=torch.uint8, device=dev), rn(2, 77, 2048), rn(2, 77, 2048))
+# the adapter module: its ~30 launches (LayerNorm, plane splits, GEMMs, column sums, mean-pool) are one PDL chain
+from pea_diffusion_b200 import adapter as A
+for prec in ("fp32", "bf16"):
+    m = A.MLP(128, 160, 128, 256, False, precision=prec).to(dev)
+    xa = rn(3, 77, 128, dt=torch.float32).requires_grad_(True)
+    x1, x2 = m(xa)
+    (x1.square().sum() + x2.square().sum()).backward()
 torch.cuda.synchronize()
 print("sanitize_smoke: all launches completed")
