@@ -1,12 +1,10 @@
 mkdir -p gpurun_out/r2
-timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -k "adapter or layernorm or rowop or split or mean or colsum" 2>&1 | tail -3
-timeout 900 python -m pytest tests/test_gpu_step.py -x -q -k "sink or accumulate or fp16 or kd" 2>&1 | tail -3
-timeout 300 python - <<'PY' 2>&1 | tail -5
-import json, torch, bench
-dev = torch.device("cuda:0")
-torch.cuda.set_device(dev)
-for i in range(3):
-    r = bench.adapter_subrun(dev, replays=30)
-    print({k: round(v, 1) for k, v in r.items() if k.endswith("_us")})
+timeout 1500 python -m pytest tests -q -m gpu 2>&1 | tail -4 > gpurun_out/r2/final_gputests.txt; cat gpurun_out/r2/final_gputests.txt
+timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('SMOKE OK')" 2>&1 | tail -3
+timeout 1200 python bench.py --gpus 1 --steps 10 --warmup 3 > gpurun_out/r2/final_bench_1gpu.json 2> gpurun_out/r2/final_bench_1gpu.err; echo bench rc=$?; tail -c 600 gpurun_out/r2/final_bench_1gpu.err
+python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/r2/final_bench_1gpu.json').read().strip().splitlines()[-1])
+r=d['roofline']
+print({k:d[k] for k in ('value','ms_per_step','gpu_launches')}, d['e2e'], 'frac',r['frac'], r.get('in_chain_marginal'), r.get('adapter_fwd_bwd'))
 PY
-timeout 300 compute-sanitizer --tool memcheck python tools/sanitize_smoke.py 2>&1 | tail -3
