@@ -734,10 +734,49 @@ def main():
     same, sums = parameter_checksums(adapter)
     loss_now = [float(v) for v in trainer.step(dbatch).float().cpu()]
 
+    def comm_in_graph_subrun(line):
+        """World > 1: the same step with the two bucket all-reduces CAPTURED in the step's graph (KDTrainer(capture_comm=True)):
+        ms/step timed like the headline, ranks compared bitwise afterwards.  Every rank runs it; a watchdog ends the process
+        (rank 0 prints the line it already has) should a collective hang."""
+        import threading
+        finished = threading.Event()
+
+        def bail():
+            if finished.wait(300):
+                return
+            if rank == 0 and line is not None:
+                line["comm_in_graph"] = {"error": "timed out after 300 s"}
+                emit(line)
+            os._exit(0)
+
+        threading.Thread(target=bail, daemon=True).start()
+        res = None
+        try:
+            trainer.close()                      # drops the graph without collectives and the taps / sink
+            args.capture_comm = True
+            t2 = make_trainer(bool(args.overlap_teacher))
+            for _ in range(3):
+                t2.step(dbatch)
+            ms = timed(lambda: t2.step(dbatch), args.steps)
+            same2, _ = parameter_checksums(adapter)
+            t2.close()                           # the graph must go before the communicator does
+            res = {"ms_per_step": ms, "value": world * B / (ms * 1e-3), "unit": UNIT, "dp_params_identical": bool(same2),
+                   "how": "forward + backward + both bucket all-reduces in ONE CUDA graph (forked branch launched from the adapter's "
+                          "backward), then the fused AdamW launch; %d steps, max over ranks" % args.steps}
+        except Exception as exc:  # noqa: BLE001
+            res = {"error": str(exc).splitlines()[0][:200]}
+        finally:
+            args.capture_comm = False
+            finished.set()
+        return res
+
+    want_cig = world > 1 and graph_mode and not args.capture_comm and not args.timed_only and not args.tiny
     if world > 1:
         dist.barrier()
     if rank != 0:
         if world > 1:
+            if want_cig:
+                comm_in_graph_subrun(None)
             dist.destroy_process_group()
         return
 
@@ -788,6 +827,9 @@ def main():
         "strong": strong,
         "dp_params_identical": bool(same), "dp_param_checksums": sums, "loss": loss_now,
     }
+    if want_cig:
+        log('collectives-in-graph sub-run')
+        line["comm_in_graph"] = comm_in_graph_subrun(line)
     if world == 1 and not args.timed_only:
         # free the training state before the isolated-kernel sweeps
         trainer.close()

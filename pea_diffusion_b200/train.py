@@ -294,10 +294,9 @@ class KDTrainer:
     ``cuda_graph=True`` captures forward + backward of the step (adapter, both UNets, loss: every kernel of this library
     and of the PyTorch shell) into ONE CUDA graph on the first call and replays it afterwards; batches are copied into the
     graph's static input buffers.  After the replay two NCCL launches reduce the flat gradient buffer (bucket by bucket, on
-    the side stream) and the fused AdamW step follows; shapes must stay fixed.  (``capture_comm=True`` puts the collectives
-    into the graph as a forked branch; with torch 2.11 / NCCL 2.28 the capture fails with cudaErrorStreamCaptureIsolation on a
-    2-GPU box, so it is off by default -- in eager mode the head's bucket IS in flight while the rest of the adapter's backward
-    runs.)
+    the side stream) and the fused AdamW step follows; shapes must stay fixed.  ``capture_comm=True`` puts the collectives
+    into the graph as a forked branch (launched from inside the adapter's backward, joined before the capture ends): the
+    replay then delivers rank-averaged gradients.  Call ``close()`` before destroying the process group in that mode.
 
     ``loss_scale`` (fp16 training, the reference's ``--precision 16``, train_sdxl_zh.sh:89): the loss is scaled before
     backward -- the fused KD pass applies the scale before rounding its gradients to fp16 --, gradients are unscaled and
@@ -435,8 +434,16 @@ class KDTrainer:
         return out.mul_(1.0 / k)
 
     def close(self) -> None:
+        """Detach from the modules and DROP the step graph.  Required before ``dist.destroy_process_group()`` when the
+        collectives were captured (``capture_comm=True``): NCCL does not tear a communicator down while a CUDA graph that
+        holds its collectives is alive -- the teardown blocks (measured: tools/nccl_capture_probe.py)."""
         self.reducer.close()
         if getattr(self.adapter, "_grad_sink", None) is self.reducer:
             self.adapter._grad_sink = None
         self.taps_s.remove()
         self.taps_t.remove()
+        if self._graph is not None:
+            torch.cuda.synchronize()
+            self._graph = None
+            self._static_out = None
+            self._static_in = {}
