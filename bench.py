@@ -262,6 +262,24 @@ def log(msg: str) -> None:
 _T0 = time.perf_counter()
 
 
+def safe_destroy_process_group(grace_s: float = 60.0) -> None:
+    """destroy_process_group() with a deadline: the results are already printed, a blocked NCCL teardown must not turn a
+    finished run into a driver timeout."""
+    import threading
+    import torch.distributed as dist
+    done = threading.Event()
+
+    def bail():
+        if not done.wait(grace_s):
+            sys.stderr.write("[bench] process-group teardown still blocked after %.0f s; exiting\n" % grace_s)
+            sys.stderr.flush()
+            os._exit(0)
+
+    threading.Thread(target=bail, daemon=True).start()
+    dist.destroy_process_group()
+    done.set()
+
+
 def emit(line: dict) -> None:
     out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
     out.write(json.dumps(line) + "\n")
@@ -777,7 +795,7 @@ def main():
         if world > 1:
             if want_cig:
                 comm_in_graph_subrun(None)
-            dist.destroy_process_group()
+            safe_destroy_process_group()
         return
 
     pk, pk_kind = peaks()
@@ -867,7 +885,7 @@ def main():
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
     emit(line)
     if world > 1:
-        dist.destroy_process_group()
+        safe_destroy_process_group()
 
 
 if __name__ == "__main__":
