@@ -1,2 +1,1 @@
-mkdir -p gpurun_out/r2
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:attn2_.*_tc_kernel -c 12 -f -o gpurun_out/r2/ncu_attn2_final2 python tools/microbench.py --only attn --filter 1024:1280,4096:640 --iters 2 --warm 1 --out gpurun_out/r2/mb_under_ncu.jsonl > gpurun_out/r2/ncu_attn2_final2.log 2>&1; echo ncu rc=$?; tail -3 gpurun_out/r2/ncu_attn2_final2.log; ls -la gpurun_out/r2/*.ncu-rep
+timeout 120 python tools/_dbg_lse.py 2>&1 | tail -12
