@@ -29,7 +29,10 @@ namespace {
 constexpr int kQT = 128;                 // query rows per tile
 constexpr int kD = 64;                   // head dim
 constexpr int kLP = 80;                  // padded key count
-constexpr int kQStages = 4;
+#ifndef PEA_Q_STAGES
+#define PEA_Q_STAGES 4
+#endif
+constexpr int kQStages = PEA_Q_STAGES;   // depth of the Q ring (16 KiB per slot; 7 is what shared memory allows)
 constexpr int kGroups = 3;                    // softmax / epilogue groups (4 warps each), tiles dealt round-robin
 constexpr int kSWarp = 2 + 4 * kGroups;       // the S = Q K^T issuer (warp 1 issues P V)
 constexpr int kThreads = 64 + kGroups * 128 + 32;
