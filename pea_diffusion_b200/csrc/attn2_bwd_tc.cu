@@ -518,7 +518,7 @@ int attn2_bwd_tc(const pea_attn2_desc* a, cudaStream_t st) {
   struct { CUtensorMap* m; const void* ptr; long long ld; } maps[3] = {{&p.tmQ, a->d_q, a->ld_q}, {&p.tmdO, a->d_do, a->ld_do}, {&p.tmdQ, a->d_dq, a->ld_dq}};
   for (auto& m : maps) {
     const uint64_t str[2] = {(uint64_t)m.ld * 2, (uint64_t)m.ld * 2 * (uint64_t)a->N};
-    int rc = encode_tmap_16bit(m.m, m.ptr, 3, dims, str, box, fp16);
+    int rc = encode_tmap_16bit(m.m, m.ptr, 3, dims, str, box, fp16, attn2_l2_promotion());
     if (rc != PEA_OK) return rc;
   }
   {
@@ -526,7 +526,7 @@ int attn2_bwd_tc(const pea_attn2_desc* a, cudaStream_t st) {
     const uint64_t kdims[3] = {(uint64_t)(voff + C), (uint64_t)a->L, (uint64_t)a->B};
     const uint64_t str[2] = {(uint64_t)a->ld_kv * 2, (uint64_t)a->bs_kv * 2};
     const uint32_t kbox[3] = {64, (uint32_t)kLP, 1};
-    int rc = encode_tmap_16bit(&p.tmKV, a->d_k, 3, kdims, str, kbox, fp16);
+    int rc = encode_tmap_16bit(&p.tmKV, a->d_k, 3, kdims, str, kbox, fp16, attn2_l2_promotion());
     if (rc != PEA_OK) return rc;
     p.voff = (int)voff;
   }

@@ -415,10 +415,10 @@ int attn2_fwd_tc(const pea_attn2_desc* a, cudaStream_t st) {
     const uint64_t dims[3] = {(uint64_t)C, (uint64_t)a->N, (uint64_t)a->B};
     const uint64_t str[2] = {(uint64_t)a->ld_q * 2, (uint64_t)a->ld_q * 2 * (uint64_t)a->N};
     const uint32_t box[3] = {64, 128, 1};
-    int rc = encode_tmap_16bit(&p.tmQ, a->d_q, 3, dims, str, box, fp16);
+    int rc = encode_tmap_16bit(&p.tmQ, a->d_q, 3, dims, str, box, fp16, attn2_l2_promotion());
     if (rc != PEA_OK) return rc;
     const uint64_t ostr[2] = {(uint64_t)a->ld_o * 2, (uint64_t)a->ld_o * 2 * (uint64_t)a->N};
-    rc = encode_tmap_16bit(&p.tmO, a->d_o, 3, dims, ostr, box, fp16);
+    rc = encode_tmap_16bit(&p.tmO, a->d_o, 3, dims, ostr, box, fp16, attn2_l2_promotion());
     if (rc != PEA_OK) return rc;
   }
   {
@@ -427,7 +427,7 @@ int attn2_fwd_tc(const pea_attn2_desc* a, cudaStream_t st) {
     const uint64_t dims[3] = {(uint64_t)(voff + C), (uint64_t)a->L, (uint64_t)a->B};
     const uint64_t str[2] = {(uint64_t)a->ld_kv * 2, (uint64_t)a->bs_kv * 2};
     const uint32_t box[3] = {64, (uint32_t)kLP, 1};
-    int rc = encode_tmap_16bit(&p.tmKV, a->d_k, 3, dims, str, box, fp16);
+    int rc = encode_tmap_16bit(&p.tmKV, a->d_k, 3, dims, str, box, fp16, attn2_l2_promotion());
     if (rc != PEA_OK) return rc;
     p.C = (int)voff;  // column offset of V inside the shared map
   }

@@ -697,7 +697,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 
 namespace {
 struct TmapKey {
-  const void* base; int rank; int fp16; uint64_t dims[3]; uint64_t strides[2]; uint32_t box[3];
+  const void* base; int rank; int fp16; uint64_t dims[3]; uint64_t strides[2]; uint32_t box[3]; int promo;
   bool operator==(const TmapKey& o) const { return memcmp(this, &o, sizeof(TmapKey)) == 0; }
 };
 struct TmapKeyHash {
@@ -710,16 +710,25 @@ struct TmapKeyHash {
 };
 }  // namespace
 
+int attn2_l2_promotion() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PEA_ATTN2_L2PROMO");
+    v = e ? atoi(e) : 128;
+  }
+  return v;
+}
+
 // Descriptors are pure functions of (pointer, shape, strides, box): a training step re-launches the same ~250 kernels on
 // the same buffers every iteration, so encodes (1-2 us of driver time each, 3-4 per launch) are cached process-wide.
 int encode_tmap_16bit(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                      const uint32_t* box, bool fp16) {
+                      const uint32_t* box, bool fp16, int l2_promotion_bytes) {
   static EncodeTiledFn fn = nullptr;
   static std::mutex mu;
   static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
   TmapKey key;
   memset(&key, 0, sizeof(key));
-  key.base = base; key.rank = rank; key.fp16 = fp16 ? 1 : 0;
+  key.base = base; key.rank = rank; key.fp16 = fp16 ? 1 : 0; key.promo = l2_promotion_bytes;
   for (int i = 0; i < rank; ++i) { key.dims[i] = dims[i]; key.box[i] = box[i]; }
   for (int i = 0; i + 1 < rank; ++i) key.strides[i] = strides_bytes[i];
   std::lock_guard<std::mutex> lock(mu);
@@ -749,7 +758,10 @@ int encode_tmap_16bit(CUtensorMap* out, const void* base, int rank, const uint64
   for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
   const CUresult rc = fn(out, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank,
                          const_cast<void*>(base), gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                         l2_promotion_bytes >= 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
+                         : l2_promotion_bytes >= 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+                         : l2_promotion_bytes >= 64  ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (rc != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d, dims %llu x %llu, stride %llu, box %u x %u)", (int)rc, rank,
               (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 1),

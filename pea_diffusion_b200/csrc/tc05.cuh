@@ -205,7 +205,12 @@ __device__ __forceinline__ bool elect_one() {
 //   dims[i]    : extent of dimension i in elements (dims[0] is the contiguous one)
 //   strides[i] : byte stride of dimension i+1 (multiple of 16)
 //   box[i]     : tile extent; box[0] * 2 bytes must be <= 128
+//   l2_promotion_bytes : granule the L2 fetches from DRAM for every 128-byte box row (256 / 128 / 64 / 0 = none).  256 suits
+//                tiles whose NEXT 128 bytes along dims[0] are the same CTA's next load (a GEMM's K-major operand); where the
+//                neighbour belongs to another CTA's work item (attention: the next head of the same rows) it only adds DRAM reads
 int encode_tmap_16bit(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                      const uint32_t* box, bool fp16);
+                      const uint32_t* box, bool fp16, int l2_promotion_bytes = 256);
+// attention tensor maps (Q, dO, O, dQ, K|V): PEA_ATTN2_L2PROMO=256|128|64|0 overrides the default for A/B runs
+int attn2_l2_promotion();
 
 }  // namespace pea
