@@ -1,16 +1,13 @@
 mkdir -p gpurun_out/r2
-for v in 256 128 64 0 256 128; do
-  PEA_ATTN2_L2PROMO=$v timeout 200 python tools/microbench.py --only attn --iters 30 --out gpurun_out/r2/mb_promo$v.jsonl > /dev/null 2>&1
-  python - "$v" <<'PY'
-import json,sys
-v=sys.argv[1]
-rows=[d for d in map(json.loads,open(f'gpurun_out/r2/mb_promo{v}.jsonl')) if d.get('op')=='attn2']
-print('promo',v, ' | '.join('%d/%d f %.1f b %.1f (%.3f)'%(x['N'],x['C'],x['fwd_us'],x['bwd_us'],x['fwdbwd_frac']) for x in rows if x['L']==77))
+timeout 1500 python -m pytest tests -q -m gpu 2>&1 | tail -4 > gpurun_out/r2/final_gputests.txt; cat gpurun_out/r2/final_gputests.txt
+timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('SMOKE OK')" 2>&1 | tail -2
+timeout 1200 python bench.py --gpus 1 --steps 10 --warmup 3 > gpurun_out/r2/final_bench_1gpu.json 2> gpurun_out/r2/final_bench_1gpu.err; echo bench rc=$?
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:attn2_.*_tc_kernel -c 4 -f -o gpurun_out/r2/ncu_attn2_big_after python tools/microbench.py --only attn --filter 16384:1280 --iters 1 --warm 1 --out gpurun_out/r2/mb_under_ncu3.jsonl > gpurun_out/r2/ncu_attn2_big_after.log 2>&1; echo ncu1 rc=$?
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:attn2_.*_tc_kernel -c 12 -f -o gpurun_out/r2/ncu_attn2_final3 python tools/microbench.py --only attn --filter 1024:1280,4096:640 --iters 2 --warm 1 --out gpurun_out/r2/mb_under_ncu4.jsonl > gpurun_out/r2/ncu_attn2_final3.log 2>&1; echo ncu2 rc=$?
+python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/r2/final_bench_1gpu.json').read().strip().splitlines()[-1])
+r=d['roofline']
+print({k:d[k] for k in ('value','ms_per_step','gpu_launches')}, d['e2e']['value'], 'frac',r['frac'], r['in_chain_marginal']['step_mix']['frac'])
+for s in r['sweep']: print(s['N'],s['C'],s['L'],s['fwd_us'],s['bwd_us'],s['fwd_frac'],s['bwd_frac'],s['fwdbwd_frac'])
 PY
-done
-for v in 256 128; do for m in fwd bwd; do
-  PEA_ATTN2_L2PROMO=$v timeout 100 python tools/chain_probe.py --mode $m --N 1024 --C 1280 2>/dev/null | python -c "
-import sys,json
-d=json.loads(sys.stdin.read()); print('promo $v',d['mode'],d['N'],d['C'],'marginal %.2f bracketed %.2f'%(d['marginal_us_per_launch'],d['bracketed_us_median']))"
-done; done
-timeout 300 python -m pytest tests/test_gpu_parity.py -x -q -k "attn2" 2>&1 | tail -2
