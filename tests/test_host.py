@@ -32,6 +32,34 @@ def test_library_exports_every_declared_symbol():
     assert "pea_gemm" in nm
 
 
+def test_ctypes_mirrors_match_the_header_layout(tmp_path):
+    """Every descriptor struct of include/pea_b200.h against its ctypes mirror in _lib.py: total size and the offset of every
+    field, taken from a C program compiled against the header (the way a maintainer binding from C / cgo would see it)."""
+    import ctypes
+    from pea_diffusion_b200 import _lib
+    mirrors = {"pea_kd_tap": _lib.KdTap, "pea_attn2_desc": _lib.Attn2Desc, "pea_gemm_desc": _lib.GemmDesc,
+               "pea_split_item": _lib.SplitItem}
+    lines = ["#include <stdio.h>", "#include <stddef.h>", '#include "pea_b200.h"', "int main(void) {"]
+    for cname, cls in mirrors.items():
+        lines.append(f'  printf("{cname} size %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname} {fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout
+    seen = 0
+    for line in out.splitlines():
+        cname, field, value = line.split()
+        cls = mirrors[cname]
+        want = ctypes.sizeof(cls) if field == "size" else getattr(cls, field).offset
+        assert int(value) == want, f"{cname}.{field}: header {value}, ctypes {want}"
+        seen += 1
+    assert seen == sum(len(c._fields_) + 1 for c in mirrors.values())
+
+
 def test_argument_errors_come_back_as_text_without_a_gpu():
     import ctypes as C
     from pea_diffusion_b200 import _lib
