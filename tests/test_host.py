@@ -60,6 +60,19 @@ def test_ctypes_mirrors_match_the_header_layout(tmp_path):
     assert seen == sum(len(c._fields_) + 1 for c in mirrors.values())
 
 
+def test_plain_c_caller_links_and_gets_errors_as_text(tmp_path):
+    """examples/abi_from_c.c: the header compiles as C99, the library links from plain C, version matches, malformed calls
+    return PEA_E* codes with a message (no GPU needed for any of that)."""
+    from pea_diffusion_b200 import _lib
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    exe = tmp_path / "abi_from_c"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "abi_from_c.c"),
+                    "-L", libdir, "-lpea_b200", f"-Wl,-rpath,{libdir}", "-o", str(exe)], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "pea_attn2_fwd with null pointers -> -1: attn2: null" in r.stdout and "pea_gemm with a bad descriptor -> -1" in r.stdout
+
+
 def test_argument_errors_come_back_as_text_without_a_gpu():
     import ctypes as C
     from pea_diffusion_b200 import _lib
